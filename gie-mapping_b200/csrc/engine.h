@@ -1,0 +1,89 @@
+// engine.h — host-side handle structs and the launch functions each .cu file provides.
+#pragma once
+#include "common.cuh"
+#include "../../include/gie_b200.h"
+#include <string>
+
+struct gie_locmap {
+    LocDev d{};                 // device view, passed by value to kernels (as the reference passes LocMap)
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int num_sms = 148;
+    float3 msg_origin{};
+    // batch-EDT scratch
+    unsigned long long *ytab = nullptr;   // [Z][ceil(Y/32)][X] (mask word, lo_prev, hi_next)
+    int32_t *g2 = nullptr;                // [Z][Y][X] plane dist_sq after the x sweep
+    int32_t *cxy = nullptr;               // [Z][Y][X] cocx | cocy << 16
+    unsigned long long *stack_scratch = nullptr;
+    size_t stack_scratch_entries = 0;
+    int edt_ctas = 0;                     // persistent grid of the sweep kernels
+    int *work_counters = nullptr;         // device: [4]
+    // staging for *_host entry points
+    float *stage_dev = nullptr;
+    size_t stage_bytes = 0;
+    // profiling
+    bool profile = false;
+    cudaEvent_t ev[GIE_ST_COUNT][2]{};
+    bool ev_valid[GIE_ST_COUNT]{};
+    long long launches = 0;
+    gie_hashmap *hm = nullptr;
+};
+
+struct gie_hashmap {
+    HashDev d{};
+    gie_locmap *lm = nullptr;
+    size_t hash_cap = 0;
+    int halo_blocks = 1;
+    size_t tab_entries = 0;
+    // wavefront queues
+    unsigned long long *qA[3]{};  // outside queues: packed global coords
+    unsigned long long *qB[3]{};
+    int32_t *qC[3]{};             // inside queue: linear local index
+    unsigned long long *cseed_key = nullptr;  // deferred C-seed pair updates (same slots as qC[0])
+    int queue_cap = 0;
+    int *counters = nullptr;      // device ints, see wave.cu
+    unsigned int *barrier = nullptr;
+    // decision scratch for wave A (parallel to the current queue)
+    int32_t *decA_dist = nullptr;
+    unsigned long long *decA_coc = nullptr;
+    unsigned long long *decA_pair = nullptr;
+    int32_t *decA_flags = nullptr;
+    uint32_t *snap_id = nullptr;  // per-queue-slot snapshot for waves B/C
+    int wave_ctas = 0;
+    int *status_host = nullptr;   // pinned
+    long long *stats_host = nullptr;  // pinned [8]
+};
+
+void gie_set_error(const std::string &msg);
+#define GIE_CUDA_CHECK(expr)                                                                           \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            gie_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                         \
+            return GIE_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+struct StageTimer {
+    gie_locmap *lm; int st;
+    StageTimer(gie_locmap *l, int s) : lm(l), st(s) { if (lm->profile) { cudaEventRecord(lm->ev[st][0], lm->stream); } }
+    ~StageTimer() { if (lm->profile) { cudaEventRecord(lm->ev[st][1], lm->stream); lm->ev_valid[st] = true; } }
+};
+
+// ogm.cu
+int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_dev, int n, int fmp, int r2);
+int gie_launch_ogm_scan2d(gie_locmap *lm, gie_hashmap *hm, const float *scan, int scan_num, float tinc, float tmin, int fmp, int r2);
+int gie_launch_ogm_vlp16(gie_locmap *lm, gie_hashmap *hm, const float *ranges, int scan_num, int ring_num, float tinc,
+                         float tmin, float pinc, float pmin, int fmp, int r2);
+int gie_launch_ogm_depth(gie_locmap *lm, gie_hashmap *hm, const float *img, int rows, int cols, float cx, float cy,
+                         float fx, float fy, int valid_nan, int fmp, int r2);
+// hashmap.cu
+int gie_hash_begin_frame(gie_hashmap *hm);                       // sets the table origin, clears touched flags
+int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct);
+int gie_launch_export(gie_hashmap *hm, int nblocks, gie_glbvoxel *out_dev);
+// edt.cu
+int gie_edt_prepare(gie_locmap *lm);
+int gie_launch_batch_edt(gie_locmap *lm);
+// wave.cu
+int gie_wave_prepare(gie_hashmap *hm);
+int gie_launch_merge(gie_hashmap *hm, int map_ct);

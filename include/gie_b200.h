@@ -1,0 +1,162 @@
+/*
+ * gie_b200.h — C ABI of the B200-native OGM + incremental-EDT engine.
+ *
+ * This is the drop-in boundary for ONE hot path of JINXER000/GIE-mapping: what
+ * VOLMAPNODE::publishMap (src/volumetric_mapper.cpp:138-224) calls per frame.
+ * Every entry point names the reference interface it replaces (file:line in the
+ * reference repo).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns GIE_OK (0) or a negative gie_status; the reference
+ *     exit(1)s / asserts instead (include/cuda_toolkit/cuda_macro.h:21-31).
+ *     gie_last_error() returns a thread-local message for the last failure.
+ *   - "_dev" pointers are device pointers on the engine's device, "_host" are
+ *     host pointers (pinned or pageable).  Output buffers are caller-owned.
+ *   - all work is enqueued on the stream given to gie_set_stream (default: the
+ *     legacy default stream, as in the reference); calls that copy to the host
+ *     synchronise that stream before returning.
+ *   - not re-entrant per handle (the reference is single-threaded per node).
+ */
+#ifndef GIE_B200_H
+#define GIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum gie_status {
+    GIE_OK = 0,
+    GIE_ERR_INVALID_ARG = -1,
+    GIE_ERR_CUDA = -2,
+    GIE_ERR_OUT_OF_BLOCKS = -3,   /* reference: throw "out of block memory" (include/vox_hash/blockalloc.h:56-58) */
+    GIE_ERR_QUEUE_OVERFLOW = -4,  /* reference: assert in parWave (src/kernel/par_wave/wave_helper.h:26-30,82-88) */
+    GIE_ERR_SIZE_UNSUPPORTED = -5 /* reference: "Local map size too big!!!" (include/map_structure/local_batch.h:54-58) */
+} gie_status;
+
+/* voxel types: include/map_structure/local_batch.h:7-10 */
+#define GIE_VOX_UNKNOWN 0
+#define GIE_VOX_FREE 1
+#define GIE_VOX_OCCUPIED 2
+#define GIE_VOX_FNT 3
+#define GIE_EMPTY_VALUE 999999 /* include/par_wave/voxmap_utils.cuh:8 */
+
+typedef struct gie_locmap gie_locmap;   /* replaces class LocMap   (include/map_structure/local_batch.h:32-569) */
+typedef struct gie_hashmap gie_hashmap; /* replaces struct GlbHashMap (include/par_wave/glb_hash_map.h:11-65)   */
+
+/* SeenDist, include/map_structure/local_batch.h:19-24 (CostMap payload, msg/CostMap.msg) */
+typedef struct gie_seendist {
+    float d;
+    unsigned char s;
+    unsigned char o;
+} gie_seendist;
+
+/* GlbVoxel in the reference's memory layout (include/par_wave/voxmap_utils.cuh:29-44), 40 bytes.
+ * Used only by gie_hashmap_export_blocks; inside the engine blocks are field-major. */
+typedef struct gie_glbvoxel {
+    unsigned char occ_val;
+    signed char vox_type;
+    int32_t update_ct;
+    int32_t coc_glb[3];
+    int32_t dist_sq;
+    int32_t wave_layer;
+    uint64_t dist_id_pair; /* (dist_sq << 32) | wave-range coc id; the reference stores the two words swapped */
+} gie_glbvoxel;
+
+const char *gie_last_error(void);
+const char *gie_version(void);
+
+/* ---- LocMap ------------------------------------------------------------------------------------- */
+/* LocMap::LocMap + create_gpu_map (local_batch.h:35-89).  Requires X,Y <= 1024, Z <= 512 (coc codec 11/11/10 bit). */
+int gie_locmap_create(gie_locmap **out, float voxel_size, int size_x, int size_y, int size_z,
+                      unsigned char occupancy_threshold, float ogm_min_h, float ogm_max_h, int cutoff_grids_sq,
+                      int fast_mode);
+/* LocMap::delete_gpu_map (local_batch.h:91-110) */
+int gie_locmap_destroy(gie_locmap *lm);
+/* cudaStream_t as void*; NULL = legacy default stream */
+int gie_set_stream(gie_locmap *lm, void *cuda_stream);
+/* trans2proj (include/cuda_toolkit/projection.h:15-33) + LocMap::calculate_pivot_origin / calculate_update_pivot
+ * (local_batch.h:128-166), as called at volumetric_mapper.cpp:144-155.  q = (w,x,y,z) body->world, t = translation. */
+int gie_locmap_set_pose(gie_locmap *lm, const float q_wxyz[4], const float t_xyz[3]);
+/* out6 = {_pvt.xyz, _update_pvt.xyz}; origin3 = _msg_origin */
+int gie_locmap_get_pivots(const gie_locmap *lm, int out6[6], float origin3[3]);
+/* LocMap::copy_ogm_2_host / copy_edt_2_host / convertCostMap (local_batch.h:370-391) */
+int gie_locmap_copy_ogm_to_host(gie_locmap *lm, signed char *glb_type_host);
+int gie_locmap_copy_edt_to_host(gie_locmap *lm, float *edt_host);
+int gie_locmap_convert_costmap(gie_locmap *lm, gie_seendist *seendist_host);
+/* raw device views for GPU consumers (LocMap::_glb_type, _edt_D, _aux, _coc_idx_aux, _dist_id_pair; local_batch.h:540-562) */
+enum gie_array { GIE_ARR_RAY_COUNT = 0, GIE_ARR_INST_TYPE = 1, GIE_ARR_GLB_TYPE = 2, GIE_ARR_EDT = 3, GIE_ARR_AUX = 4,
+                 GIE_ARR_COC_AUX = 5, GIE_ARR_PAIR = 6 };
+int gie_locmap_device_ptr(gie_locmap *lm, int which, void **dev_ptr, size_t *bytes);
+int gie_locmap_download(gie_locmap *lm, int which, void *host_out);
+/* test hook: overwrite _glb_type (N bytes) so the batch EDT can be driven directly */
+int gie_locmap_upload_glb_type(gie_locmap *lm, const signed char *glb_type_host);
+
+/* ---- GlbHashMap --------------------------------------------------------------------------------- */
+/* GlbHashMap::GlbHashMap + setLocMap (src/kernel/par_wave/glb_hash_map.cu:9-56) */
+int gie_hashmap_create(gie_hashmap **out, gie_locmap *lm, int bucket_max, int block_max);
+int gie_hashmap_destroy(gie_hashmap *hm);
+
+/* ---- OGM: *_FAST::localOGMKernels / *MapMaker::updateLocalOGM ------------------------------------
+ * The reference passes `int3* VB_keys_loc_D` (12 B/voxel key array owned by GlbHashMap); here the hash map
+ * handle is passed instead and the engine records touched blocks in a bitmap. */
+/* PNTCLD_RAYCAST::localOGMKernels (src/kernel/point_cloud/pntcld_raycast.cu:105-117); pts = float3[n], sensor frame */
+int gie_ogm_pointcloud_dev(gie_locmap *lm, gie_hashmap *hm, const float *pts_dev, int n, int for_motion_planner,
+                           int rbt_r2_grids);
+/* PntcldMapMaker::updateLocalOGM (src/pntcld_map_maker.cpp:63-73): H2D copy + kernels */
+int gie_ogm_pointcloud_host(gie_locmap *lm, gie_hashmap *hm, const float *pts_host, int n, int for_motion_planner,
+                            int rbt_r2_grids);
+/* HOKUYO_FAST::localOGMKernels (src/kernel/hokuyo/hokuyo_fast.cu:83-91); ScanParam: include/.../hokuyo/scan_param.h */
+int gie_ogm_scan2d_dev(gie_locmap *lm, gie_hashmap *hm, const float *scan_dev, int scan_num, float theta_inc,
+                       float theta_min, int for_motion_planner, int rbt_r2_grids);
+int gie_ogm_scan2d_host(gie_locmap *lm, gie_hashmap *hm, const float *scan_host, int scan_num, float theta_inc,
+                        float theta_min, int for_motion_planner, int rbt_r2_grids);
+/* VLP_FAST::localOGMKernels (src/kernel/vlp16/vlp16_fast.cu:89-97); ranges = float[ring_num*scan_num] horizontal range */
+int gie_ogm_vlp16_dev(gie_locmap *lm, gie_hashmap *hm, const float *ranges_dev, int scan_num, int ring_num,
+                      float theta_inc, float theta_min, float phi_inc, float phi_min, int for_motion_planner,
+                      int rbt_r2_grids);
+int gie_ogm_vlp16_host(gie_locmap *lm, gie_hashmap *hm, const float *ranges_host, int scan_num, int ring_num,
+                       float theta_inc, float theta_min, float phi_inc, float phi_min, int for_motion_planner,
+                       int rbt_r2_grids);
+/* REALSENSE_FAST::localOGMKernels (src/kernel/realsense/realsense_fast.cu:97-105); depth = float[rows*cols] metres */
+int gie_ogm_depth_dev(gie_locmap *lm, gie_hashmap *hm, const float *depth_dev, int rows, int cols, float cx, float cy,
+                      float fx, float fy, int valid_nan, int for_motion_planner, int rbt_r2_grids);
+int gie_ogm_depth_host(gie_locmap *lm, gie_hashmap *hm, const float *depth_host, int rows, int cols, float cx,
+                       float cy, float fx, float fy, int valid_nan, int for_motion_planner, int rbt_r2_grids);
+
+/* GlbHashMap::updateHashOGM (glb_hash_map.cu:115-143) incl. allocHashTB (:58-113).  External-obstacle AABBs
+ * (Ext_Obs_Wrapper) are not supported: the reference ships them deactivated (src/kernel/pre_map/pre_map.cu:85). */
+int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct);
+/* EDT_OCC::batchEDTUpdate (src/kernel/edt/local_edt.cu:7-28); cuTT plans are not needed */
+int gie_edt_batch_update(gie_locmap *lm);
+/* GlbHashMap::mergeNewObsv (glb_hash_map.cu:146-207) */
+int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct);
+/* waits for the stream and returns the sticky device-side status (queue overflow, out of blocks) */
+int gie_sync(gie_hashmap *hm);
+
+/* number of allocated voxel blocks; export in the reference's GlbVoxel layout (README.md:163-170 contract):
+ * keys_host = int[3*n], voxels_host = gie_glbvoxel[512*n] with voxel index (x&7)*64+(y&7)*8+(z&7) */
+int gie_hashmap_num_blocks(gie_hashmap *hm, int *n);
+int gie_hashmap_export_blocks(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel *voxels_host, int max_blocks);
+/* frontier sizes / BFS levels of the last merge: {fA, fB, fC, levelsA, levelsB, levelsC, fB_after_A, fC_after_B} */
+int gie_hashmap_wave_stats(gie_hashmap *hm, int64_t out8[8]);
+
+/* ---- measurement -------------------------------------------------------------------------------- */
+/* When enabled, CUDA events bracket each stage on the engine stream. */
+enum gie_stage { GIE_ST_OGM = 0, GIE_ST_HASH_MERGE = 1, GIE_ST_EDT_PACK = 2, GIE_ST_EDT_X = 3, GIE_ST_EDT_Z = 4,
+                 GIE_ST_MARK_FRONTIER = 5, GIE_ST_WAVES = 6, GIE_ST_COMMIT = 7, GIE_ST_COUNT = 8 };
+int gie_profile_enable(gie_locmap *lm, int on);
+/* milliseconds of the last frame's stages (synchronises the stream) */
+int gie_profile_last(gie_locmap *lm, float ms_out[GIE_ST_COUNT]);
+/* number of kernels this library launched since creation */
+int gie_launch_count(gie_locmap *lm, long long *n);
+
+/* warmupCuda (include/warmup.h:9) */
+int gie_warmup(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIE_B200_H */

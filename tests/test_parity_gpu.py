@@ -1,0 +1,129 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the CPU oracle on the same seeded inputs.
+Bit-exact for every integer / byte output; _edt_D compared as floats bit-exact too (both are IEEE sqrtf of the same int)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp_frame(gie, mp, om, tag):
+    lm = mp.loc_map
+    mp.hash_map.sync()
+    assert (lm.pivots()[0] == om.pivots()[0]).all() and (lm.pivots()[1] == om.pivots()[1]).all(), tag
+    for which, ref, name in [(gie.ARR_GLB_TYPE, om.glb_type, "glb_type"), (gie.ARR_RAY_COUNT, om.ray_count, "ray_count"),
+                             (gie.ARR_INST_TYPE, om.inst_type, "inst_type"), (gie.ARR_AUX, om.aux, "aux"),
+                             (gie.ARR_COC_AUX, om.coc_aux, "coc_aux"), (gie.ARR_PAIR, om.pair, "pair")]:
+        got = lm.download(which)
+        bad = int((got != ref).sum())
+        assert bad == 0, f"{tag}: {name} differs in {bad} voxels"
+    known = om.glb_type != 0
+    got = lm.download(gie.ARR_EDT)
+    assert np.array_equal(got[known].view(np.uint32), om.edt[known].view(np.uint32)), f"{tag}: edt differs"
+    assert mp.hash_map.wave_stats() == om.stats(), f"{tag}: {mp.hash_map.wave_stats()} vs {om.stats()}"
+
+
+def _cmp_blocks(mp, om, tag):
+    gk, gv = mp.hash_map.export_blocks()
+    ok, ov = om.export_blocks()
+    # the engine may hold extra (all-UNKNOWN) blocks only if the oracle does too: same key set
+    go = np.lexsort((gk[:, 2], gk[:, 1], gk[:, 0]))
+    oo = np.lexsort((ok[:, 2], ok[:, 1], ok[:, 0]))
+    assert np.array_equal(gk[go], ok[oo]), f"{tag}: block key sets differ ({len(gk)} vs {len(ok)})"
+    for field in ["occ_val", "vox_type", "coc_glb", "dist_sq", "dist_id_pair", "update_ct", "wave_layer"]:
+        assert np.array_equal(gv[go][field], ov[oo][field]), f"{tag}: block field {field} differs"
+
+
+@pytest.mark.parametrize("name,size,cutoff,dynamic,nframes", [
+    ("cfg4", (48, 48, 24), 64, True, 8),
+    ("cfg4", (64, 40, 33), 100, True, 6),      # ragged: X,Y,Z not multiples of 32 / 8
+    ("cfg1", (64, 64, 16), 100, False, 5),
+    ("cfg2", (64, 64, 32), 49, True, 6),
+    ("cfg3", (64, 64, 32), 100, True, 6),
+])
+def test_pipeline_parity(gie, oracle, name, size, cutoff, dynamic, nframes):
+    cfg = gie.scenes.small_config(name, size, cutoff_grids_sq=cutoff)
+    frames = gie.scenes.make_frames(cfg, nframes, dynamic=dynamic)
+    mp = gie.Mapper(cfg)
+    om = oracle.OracleMapper(cfg)
+    try:
+        for k, f in enumerate(frames):
+            mp.integrate(f)
+            om.integrate(f)
+            got = mp.loc_map.download(gie.ARR_GLB_TYPE)
+            assert np.array_equal(got, om.glb_type), f"{name} frame {k}: glb_type after OGM merge differs in {(got != om.glb_type).sum()}"
+            mp.update_edt()
+            om.update_edt()
+            _cmp_frame(gie, mp, om, f"{name} frame {k}")
+        _cmp_blocks(mp, om, name)
+    finally:
+        mp.close()
+        om.close()
+
+
+def test_motion_planner_sphere(gie, oracle):
+    for name in ["cfg4", "cfg3"]:
+        cfg = gie.scenes.small_config(name, (48, 48, 24), cutoff_grids_sq=64)
+        cfg["for_motion_planner"], cfg["robot_r2_grids"] = True, 12
+        frames = gie.scenes.make_frames(cfg, 3)
+        mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+        try:
+            for k, f in enumerate(frames):
+                mp.publishMap(f)
+                om.publishMap(f)
+                _cmp_frame(gie, mp, om, f"{name} sphere frame {k}")
+            cm = mp.loc_map.convertCostMap()
+            assert np.array_equal(cm["d"].reshape(om.edt.shape).view(np.uint32), mp.loc_map.download(gie.ARR_EDT).view(np.uint32))
+            assert np.array_equal(cm["o"].reshape(om.edt.shape) != 0, om.glb_type != 0)
+        finally:
+            mp.close()
+            om.close()
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (40, 50, 33), (7, 5, 3), (1, 64, 64), (64, 128, 96)])
+@pytest.mark.parametrize("density", [0.0, 1e-4, 0.01, 0.3])
+def test_batch_edt_parity(gie, oracle, shape, density):
+    Z, Y, X = shape
+    rng = np.random.RandomState(Z * 1000 + Y + int(density * 1e4))
+    t = np.where(rng.rand(Z, Y, X) < density, 2, rng.randint(0, 2, (Z, Y, X))).astype(np.int8)
+    lm = gie.LocMap(0.1, (X, Y, Z), cutoff_grids_sq=100)
+    om = oracle.OracleMapper(dict(local_size=(X, Y, Z), voxel_width=0.1, cutoff_grids_sq=100))
+    try:
+        lm.upload_glb_type(t)
+        lm.batchEDTUpdate()
+        om.set_glb_type(t)
+        om.batch_edt()
+        assert np.array_equal(lm.download(gie.ARR_AUX), om.aux)
+        assert np.array_equal(lm.download(gie.ARR_COC_AUX), om.coc_aux)
+    finally:
+        lm.close()
+        om.close()
+
+
+def test_batch_edt_large_property(gie):
+    """256^3: exactness checked through properties that do not need the O(N) oracle: occupied voxels have distance 0 and
+    point at themselves; every voxel's coc is occupied and |voxel - coc|^2 == dist; distance is 1-Lipschitz in sqrt."""
+    X = Y = Z = 256
+    rng = np.random.RandomState(7)
+    t = np.ones((Z, Y, X), np.int8)
+    idx = rng.randint(0, X, size=(4000, 3))
+    t[idx[:, 2], idx[:, 1], idx[:, 0]] = 2
+    lm = gie.LocMap(0.1, (X, Y, Z), cutoff_grids_sq=100)
+    try:
+        lm.upload_glb_type(t)
+        lm.batchEDTUpdate()
+        d = lm.download(gie.ARR_AUX).astype(np.int64)
+        c = lm.download(gie.ARR_COC_AUX).astype(np.int64)
+    finally:
+        lm.close()
+    cx, cy, cz = c & 0x7ff, (c >> 11) & 0x7ff, (c >> 22) & 0x3ff
+    zz, yy, xx = np.meshgrid(np.arange(Z), np.arange(Y), np.arange(X), indexing="ij")
+    assert (t[cz, cy, cx] == 2).all()
+    assert np.array_equal((xx - cx) ** 2 + (yy - cy) ** 2 + (zz - cz) ** 2, d)
+    assert (d[t == 2] == 0).all() and (d[t != 2] > 0).all()
+    r = np.sqrt(d)
+    for ax in range(3):
+        assert np.abs(np.diff(r, axis=ax)).max() <= 1.0 + 1e-9
+    # exact against scipy's EDT
+    from scipy import ndimage
+    ref = ndimage.distance_transform_edt(t != 2) ** 2
+    assert np.array_equal(np.rint(ref).astype(np.int64), d)
