@@ -148,7 +148,7 @@ __device__ __forceinline__ int gie_hash_find(const HashDev &h, int3 key)
         if (cur == k) {
             int v;
             // the value is published after the key; spin until visible (insert is two stores)
-            while ((v = __ldcg(&h.vals[s])) < 0) { }
+            while ((v = *(volatile int32_t *)&h.vals[s]) < 0) { }
             return v;
         }
         if (cur == ~0ULL) return -1;

@@ -47,7 +47,7 @@ __device__ int hash_insert(const HashDev &h, int3 key)
         }
         if (cur == k) {
             int v;
-            while ((v = __ldcg(&h.vals[s])) < 0) { }
+            while ((v = *(volatile int32_t *)&h.vals[s]) < 0) { }   // volatile: the publish comes from another thread
             return v == 0x7fffffff ? -1 : v;
         }
         s = (s + 1) & h.cap_mask;
