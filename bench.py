@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the per-frame OGM + hash merge + batch EDT + wavefront merge path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg4] [--impl ours|reference]
+
+A "step" is one frame of VOLMAPNODE::publishMap's hot path (reference src/volumetric_mapper.cpp:138-224) on a moving
+synthetic sensor (gie-mapping_b200/scenes.py).  N=1 runs the headline configuration cfg4 (512^3 @ 0.1 m, 65 536-point
+OS-32 scan, full wavefronts).  N>1 runs N independent replicas, one per GPU (weak scaling; the sharded 1024^3
+configuration is not built yet — DESIGN.md §8).
+
+  value      frames/s with the sensor frames already resident in HBM (CUDA events on the launch stream)
+  e2e        frames/s through the host-buffer C ABI: pinned host points -> H2D inside the timed region, and a D2H read of
+             the frame's result record (device status + wavefront statistics)
+  roofline   algorithmic bytes of the dominant kernel / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the C oracle (oracle/gie_oracle.c, a port) on a bounded sample, one host core
+
+--impl reference times the reference's own CUDA sources recompiled for sm_100a (oracle/_ref/ref_driver_fast: original
+Release flags, cuTT replaced by a gather shim) on the same frames; the reference has no CPU implementation of this path.
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_pkg():
+    if "gie_mapping_b200" in sys.modules:
+        return sys.modules["gie_mapping_b200"]
+    pkg_dir = os.path.join(ROOT, "gie-mapping_b200")
+    spec = importlib.util.spec_from_file_location("gie_mapping_b200", os.path.join(pkg_dir, "__init__.py"),
+                                                  submodule_search_locations=[pkg_dir])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["gie_mapping_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+# algorithmic bytes per voxel of each full-volume kernel
+ALGO_BYTES = {
+    "hash_merge": 15.0,     # count R4+W4, inst R1+W1, glb_type W1, voxel occ/type R2+W2
+    "edt_pack": 1.25,       # glb_type R1, ytab W0.25
+    "edt_x": 8.25,          # ytab R0.25, g2 W4, cxy W4
+    "edt_z": 16.0,          # g2 R4, cxy R4 (gather), aux W4, coc_aux W4
+    "mark_frontier": 50.0,  # mark: R aux4 coc4 type1 dist4 coc8, W pair8 (29); frontiers: R pair8 type1 +nbrs(L1/L2), W wave_layer4 (21)
+    "commit": 33.0,         # R type1 pair8, W coc8 dist4 pair8 edt4
+}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([p.strip() for p in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx.append(float(s[1]))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def cpu_baseline(gie, cfg, frames):
+    """C oracle on a bounded sample: same sensor frames, local volume cropped to 256^3 (1/8 of the voxels), 2 frames."""
+    from oracle import oracle_py
+    sub = dict(cfg)
+    X, Y, Z = cfg["local_size"]
+    sub["local_size"] = (min(X, 256), min(Y, 256), min(Z, 256))
+    om = oracle_py.OracleMapper(sub)
+    n = 2
+    t0 = time.perf_counter()
+    for f in frames[:n]:
+        om.publishMap(f)
+    dt = time.perf_counter() - t0
+    om.close()
+    vox = sub["local_size"][0] * sub["local_size"][1] * sub["local_size"][2]
+    full = X * Y * Z
+    fps_equiv = (vox * n / dt) / full
+    return {"value": fps_equiv, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{n} frames of the {cfg['name']} sensor stream on a {sub['local_size']} crop of the local volume "
+                      f"({dt:.1f} s CPU); frames/s scaled by voxel count to {cfg['local_size']}",
+            "mvoxels_per_s": vox * n / dt / 1e6}
+
+
+def run_reference(args, gie, cfg, frames):
+    from oracle import ref_io
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    line = {"impl": "reference", "metric": "EDT+OGM frames/sec", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
+            "data": "synthetic"}
+    X, Y, Z = cfg["local_size"]
+    nvox = X * Y * Z
+    if ref_io.available("fast"):
+        t = ref_io.run(cfg, frames, "fast", timing=True)
+        t = t[args.warmup:]
+        ms = float(np.mean([a + b for a, b in t]))
+        fps = 1000.0 / ms
+        pts_bytes = int(np.mean([f[ref_io.PAYLOAD_KEY[cfg["sensor"]]].nbytes for f in frames]))
+        line.update({"value": fps, "ms_per_step": ms, "mvoxels_per_s": fps * nvox / 1e6,
+                     "stage_ms": {"ogm_half": float(np.mean([a for a, _ in t])), "edt_half": float(np.mean([b for _, b in t]))},
+                     "config": {"workload": f"{cfg['name']}: {X}x{Y}x{Z} @ {cfg['voxel_width']} m, {cfg['sensor']}, "
+                                            f"cutoff_grids_sq={cfg['cutoff_grids_sq']}, fast_mode={cfg['fast_mode']}"},
+                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+                                      "sample": "the reference's own CUDA sources (unmodified, Release flags, cuTT replaced by a gather "
+                                                "shim) recompiled for sm_100a and run on the GPU; it has no CPU implementation; "
+                                                "host-timed per frame with cudaDeviceSynchronize as the reference does"},
+                     "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": pts_bytes, "d2h_bytes_per_step": 0}})
+    else:
+        cb = cpu_baseline(gie, cfg, frames)
+        line.update({"value": cb["value"], "ms_per_step": 1000.0 / cb["value"], "config": {"workload": cfg["name"]},
+                     "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="cfg4")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    gie = load_pkg()
+    cfg = gie.scenes.make_config(args.config)
+    nframes = args.warmup + args.steps
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    frames = gie.scenes.make_frames(cfg, nframes, seed=42 + rank)
+    if args.impl == "reference":
+        run_reference(args, gie, cfg, frames)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+
+    key = {"pointcloud": "points", "scan2d": "scan", "vlp16": "ranges", "depth": "depth"}[cfg["sensor"]]
+    host_in = [torch.from_numpy(np.ascontiguousarray(f[key], np.float32)).pin_memory() for f in frames]
+    dev_in = [h.to(dev) for h in host_in]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_pass(device_resident):
+        """Fresh map, W warm-up frames, K timed frames.  Returns ms/step (max over ranks) and the mapper."""
+        mp = gie.Mapper(cfg)
+        mp.loc_map.set_stream(stream.cuda_stream)
+        result = torch.zeros(9, dtype=torch.int64).pin_memory()
+        for k in range(args.warmup):
+            mp.publishMap(frames[k], device_input=dev_in[k].data_ptr() if device_resident else None)
+        mp.hash_map.sync()
+        barrier()
+        l0 = mp.loc_map.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for k in range(args.warmup, nframes):
+            if device_resident:
+                mp.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+            else:
+                f = dict(frames[k])
+                f[key] = host_in[k].numpy()
+                mp.publishMap(f)               # H2D copy of the frame happens inside the C ABI call
+                mp.hash_map.sync()             # D2H of the device status word
+                st = mp.hash_map.wave_stats()  # D2H result record (pinned, written by the device)
+                result[0] = st["fC"]
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        launches = mp.loc_map.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, mp
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ms_dev, launches, mp = run_pass(True)
+    # stage profile on the same map, continuing the stream of frames (not part of the timed region)
+    mp.loc_map.profile_enable(True)
+    prof = {}
+    reps = min(5, args.steps)
+    for k in range(nframes - reps, nframes):
+        mp.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+        for name, v in mp.loc_map.profile_last().items():
+            prof[name] = prof.get(name, 0.0) + v / reps
+    wave_stats = mp.hash_map.wave_stats()
+    nblocks = mp.hash_map.num_blocks()
+    mp.close()
+    ms_e2e, _, mp2 = run_pass(False)
+    mp2.close()
+    sampler.stop()
+    clocks = sampler.summary()
+
+    X, Y, Z = cfg["local_size"]
+    nvox = X * Y * Z
+    fps = world * 1000.0 / ms_dev
+    fps_e2e = world * 1000.0 / ms_e2e
+    peak, peak_src = measured_peak()
+    dom = max(ALGO_BYTES, key=lambda k: prof.get(k, 0.0))
+    achieved = ALGO_BYTES[dom] * nvox / (prof[dom] * 1e-3) / 1e9 if prof.get(dom, 0) > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_voxel": ALGO_BYTES[dom],
+                "kernel_ms": prof[dom],
+                "per_kernel": {k: {"ms": prof.get(k, 0.0),
+                                   "achieved_gbs": (ALGO_BYTES[k] * nvox / (prof[k] * 1e-3) / 1e9) if prof.get(k, 0) > 0 else None}
+                               for k in ALGO_BYTES}}
+    tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(dom)
+        except Exception:
+            pass
+    line = {"metric": "EDT+OGM frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32+f32", "data": "synthetic",
+            "config": {"workload": f"{cfg['name']}: {X}x{Y}x{Z} @ {cfg['voxel_width']} m, {cfg['sensor']} "
+                                   f"{int(np.mean([h.numel() for h in host_in])) // 3 if cfg['sensor'] == 'pointcloud' else host_in[0].numel()} "
+                                   f"values/frame, cutoff_grids_sq={cfg['cutoff_grids_sq']}, fast_mode={cfg['fast_mode']}",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas",
+                       "l2": "per-frame working set (>= 3 GB) exceeds the 126 MB L2; no explicit flush"},
+            "mvoxels_per_s": fps * nvox / 1e6,
+            "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(np.mean([h.numel() * 4 for h in host_in])) + 28, "d2h_bytes_per_step": 4 + 64},
+            "gpu_launches": int(launches),
+            "stage_ms": prof, "wave_stats": wave_stats, "blocks": nblocks,
+            "roofline": roofline, "clocks": clocks}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(gie, cfg, frames)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
