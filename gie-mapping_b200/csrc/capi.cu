@@ -131,7 +131,7 @@ int gie_locmap_destroy(gie_locmap *lm)
     LocDev &m = lm->d;
     cudaFree(m.ray_count); cudaFree(m.inst_type); cudaFree(m.glb_type); cudaFree(m.edt); cudaFree(m.aux);
     cudaFree(m.coc_aux); cudaFree(m.wave_layer); cudaFree(m.pair);
-    cudaFree(lm->ytab); cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
+    cudaFree(lm->ytab); cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->col_list); cudaFree(lm->edt_meta); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
     cudaFree(lm->stage_dev);
     for (int i = 0; i < GIE_ST_COUNT; i++) for (int j = 0; j < 2; j++) if (lm->ev[i][j]) cudaEventDestroy(lm->ev[i][j]);
     delete lm;

@@ -9,50 +9,89 @@
 // argmin_k (z-k)^2 + g2(k) ties -> smallest k.  Output _aux = dist_sq, _coc_idx_aux = x | y<<11 | z<<22 (local).
 //
 // Mechanism (no transposes, no global s/t/g arrays):
-//   k_edt_ycols : per (x,z) column packs OCCUPIED bits along y into 32-bit words and, per word, the nearest set bit
-//                 below / above the word  -> ytab[z][wy][x] (0.25 B/voxel).  The y pass itself is never materialised.
-//   k_edt_xsweep: one warp = 32 consecutive rows y of one slice z.  Lane y derives g1(u,y) from the warp-uniform ytab
-//                 entry of column u with two bit scans, runs the lower-envelope scan along x with the stack top in
-//                 registers and the body in a per-warp, lane-interleaved scratch ring (L2 resident), and writes its
-//                 outputs through a 32x16 shared-memory tile so that global stores are x-contiguous.
-//   k_edt_zsweep: one warp = 32 consecutive x of one row y; same scan along z, naturally coalesced; gathers (cocx,cocy)
-//                 of the winning slice and emits the final packed result.
-// Persistent CTAs (multiple of the SM count) pull work items from an atomic counter.
+//   k_edt_ycols : one CTA per slice z, one thread per column x.  Packs OCCUPIED bits along y into 32-bit words plus, per
+//                 word, the nearest set bit below / above it -> ytab[z][wy][x] (0.25 B/voxel); the y pass is never
+//                 materialised.  Also compacts the columns of the slice that hold an obstacle.  A column without one is
+//                 the reference's "_max_width" sentinel for EVERY row of the slice and can never win the x sweep while a
+//                 real column exists ((X+Y+Z)^2 exceeds any real candidate), so the x sweep only visits real columns, and
+//                 slices without any obstacle are skipped altogether (the z sweep never reads them).
+//   k_edt_xsweep: one warp = 32 consecutive rows y of one real slice.  Lane y derives g1(u,y) from the warp-uniform ytab
+//                 entry with two bit scans, runs the lower-envelope scan along x (stack top in registers, the next 16
+//                 entries per lane in a shared-memory ring, deeper entries in an L2-resident per-warp scratch), and emits
+//                 its outputs through a 32x16 shared-memory tile so that global stores are x-contiguous.
+//   k_edt_zsweep: one warp = 32 consecutive x of one row y; the same scan along z over the real slices only, naturally
+//                 coalesced; gathers (cocx,cocy) of the winning slice and writes the final packed result.
+// Persistent CTAs (a multiple of the SM count) pull work items from an atomic counter.
 #include "engine.h"
 
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
+constexpr int RING = 16;      // stack entries per lane kept in shared memory
+constexpr int XS_SMEM_INTS_PER_WARP = 2 * 32 * 17 + 2 * RING * 32;
+constexpr int XS_SMEM_BYTES = WARPS_PER_CTA * XS_SMEM_INTS_PER_WARP * 4;
 
-__global__ void __launch_bounds__(128) k_edt_ycols(LocDev m, unsigned long long *__restrict__ ytab, int WY)
+__global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long *__restrict__ ytab, int WY,
+                                                    int *__restrict__ col_list, int *__restrict__ n_cols)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int z = blockIdx.y;
-    if (x >= m.X) return;
-    const int8_t *col = m.glb_type + (size_t)z * m.X * m.Y + x;
-    unsigned long long *out = ytab + (size_t)z * WY * m.X + x;
-    int lo_prev = 0xffff;
-    for (int wy = 0; wy < WY; wy++) {
-        uint32_t w = 0;
-        int ybase = wy * 32;
-        int n = min(32, m.Y - ybase);
+    __shared__ int warp_cnt[32];
+    const int x = threadIdx.x, z = blockIdx.x;
+    const int lane = x & 31, wid = x >> 5;
+    bool any = false;
+    if (x < m.X) {
+        const int8_t *col = m.glb_type + (size_t)z * m.X * m.Y + x;
+        unsigned long long *out = ytab + (size_t)z * WY * m.X + x;
+        int lo_prev = 0xffff;
+        for (int wy = 0; wy < WY; wy++) {
+            uint32_t w = 0;
+            int ybase = wy * 32;
+            int n = min(32, m.Y - ybase);
 #pragma unroll 8
-        for (int b = 0; b < n; b++)
-            w |= (uint32_t)(col[(size_t)(ybase + b) * m.X] == GIE_VOX_OCCUPIED) << b;
-        out[(size_t)wy * m.X] = (unsigned long long)w | ((unsigned long long)lo_prev << 32);
-        if (w) lo_prev = ybase + 31 - __clz(w);
+            for (int b = 0; b < n; b++)
+                w |= (uint32_t)(col[(size_t)(ybase + b) * m.X] == GIE_VOX_OCCUPIED) << b;
+            out[(size_t)wy * m.X] = (unsigned long long)w | ((unsigned long long)lo_prev << 32);
+            if (w) { lo_prev = ybase + 31 - __clz(w); any = true; }
+        }
+        if (any) {   // a column without obstacles is never visited by the x sweep
+            int hi_next = 0xffff;
+            for (int wy = WY - 1; wy >= 0; wy--) {
+                unsigned long long e = out[(size_t)wy * m.X];
+                out[(size_t)wy * m.X] = e | ((unsigned long long)hi_next << 48);
+                uint32_t w = (uint32_t)e;
+                if (w) hi_next = wy * 32 + __ffs(w) - 1;
+            }
+        }
     }
-    int hi_next = 0xffff;
-    for (int wy = WY - 1; wy >= 0; wy--) {
-        unsigned long long e = out[(size_t)wy * m.X];
-        out[(size_t)wy * m.X] = e | ((unsigned long long)hi_next << 48);
-        uint32_t w = (uint32_t)e;
-        if (w) hi_next = wy * 32 + __ffs(w) - 1;
-    }
+    // ordered compaction of the real columns of this slice
+    unsigned bal = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    int before = 0, total = 0;
+    for (int i = 0; i < nw; i++) { int c = warp_cnt[i]; if (i < wid) before += c; total += c; }
+    if (any) col_list[(size_t)z * m.X + before + __popc(bal & ((1u << lane) - 1))] = x;
+    if (x == 0) n_cols[z] = total;
 }
 
-// exact floor(num/den) for 0 <= num < 2^24, 0 < den < 2^12 (see the argument in DESIGN.md §4.2: num >= 0 always)
+// ordered list of the slices that hold at least one obstacle
+__global__ void __launch_bounds__(1024) k_edt_slices(int Z, const int *__restrict__ n_cols, int *__restrict__ slice_list,
+                                                     int *__restrict__ n_slices)
+{
+    __shared__ int warp_cnt[32];
+    const int z = threadIdx.x, lane = z & 31, wid = z >> 5;
+    bool any = z < Z && n_cols[z] > 0;
+    unsigned bal = __ballot_sync(0xffffffffu, any);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    int before = 0, total = 0;
+    for (int i = 0; i < nw; i++) { int c = warp_cnt[i]; if (i < wid) before += c; total += c; }
+    if (any) slice_list[before + __popc(bal & ((1u << lane) - 1))] = z;
+    if (z == 0) *n_slices = total;
+}
+
+// exact floor(num/den) for 0 <= num < 2^24, 0 < den < 2^12 (num >= 0 is guaranteed)
 __device__ __forceinline__ int floor_div(int num, int den)
 {
     int q = (int)__fdividef((float)num, (float)den);
@@ -61,34 +100,59 @@ __device__ __forceinline__ int floor_div(int num, int den)
     return q;
 }
 
+// Envelope stack of one lane.  Entry = (h, s | t<<10 | cy<<20).  The top lives in registers; entries [base, q] live in a
+// shared-memory ring (conflict free: bank == lane), entries below `base` in the per-warp global scratch.
 struct Top { int s, t, h, cy; };
-__device__ __forceinline__ unsigned long long pack_entry(const Top &e)
-{
-    return (unsigned long long)(uint32_t)e.h | ((unsigned long long)e.s << 24) | ((unsigned long long)e.t << 35) |
-           ((unsigned long long)e.cy << 46);
-}
-__device__ __forceinline__ Top unpack_entry(unsigned long long p)
-{
-    Top e;
-    e.h = (int)(p & 0xffffff); e.s = (int)((p >> 24) & 0x7ff); e.t = (int)((p >> 35) & 0x7ff); e.cy = (int)((p >> 46) & 0x7ff);
-    return e;
-}
+struct LaneStack {
+    int *sh;          // smem: sh[slot*32] = h words, sb = sh + RING*32 the packed words (lane offset applied)
+    int *sb;
+    uint2 *g;         // global scratch, lane offset applied, stride 32
+    int base;
+    __device__ __forceinline__ void put(int q, const Top &e)
+    {
+        if (q < base) base = q;
+        else if (q - base >= RING) {
+            int sl = (base & (RING - 1)) * 32;
+            g[base * 32] = make_uint2((uint32_t)sh[sl], (uint32_t)sb[sl]);
+            base++;
+        }
+        int sl = (q & (RING - 1)) * 32;
+        sh[sl] = e.h;
+        sb[sl] = e.s | (e.t << 10) | (e.cy << 20);
+    }
+    __device__ __forceinline__ Top get(int q)
+    {
+        if (q < base) {   // refill half a ring with independent loads
+            int nb = max(0, q - RING / 2 + 1);
+            for (int i = nb; i <= q; i++) {
+                uint2 v = g[i * 32];
+                int sl = (i & (RING - 1)) * 32;
+                sh[sl] = (int)v.x; sb[sl] = (int)v.y;
+            }
+            base = nb;
+        }
+        int sl = (q & (RING - 1)) * 32;
+        int b = sb[sl];
+        Top e;
+        e.h = sh[sl]; e.s = b & 0x3ff; e.t = (b >> 10) & 0x3ff; e.cy = b >> 20;
+        return e;
+    }
+};
 
 // one step of the lower-envelope construction (EDTphase2/3 forward loops, local_edt_core.h:93-115 / :146-168)
-__device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, int &q, Top &top,
-                                              unsigned long long *__restrict__ stack /* + lane */)
+__device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, int &q, Top &top, LaneStack &st)
 {
     while (q >= 0) {
         int a = top.t - top.s, b = top.t - u;
         if (a * a + top.h > b * b + h_u) {
             q--;
-            if (q >= 0) top = unpack_entry(stack[q * 32]);
+            if (q >= 0) top = st.get(q);
         } else break;
     }
     if (q < 0) {
         q = 0;
         top.s = u; top.t = 0; top.h = h_u; top.cy = cy_u;
-        stack[0] = pack_entry(top);
+        st.put(0, top);
     } else {
         int num = u * u - top.s * top.s + h_u - top.h;
         int den = 2 * (u - top.s);
@@ -96,66 +160,86 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
         if (w < L) {
             q++;
             top.s = u; top.t = w; top.h = h_u; top.cy = cy_u;
-            stack[q * 32] = pack_entry(top);
+            st.put(q, top);
         }
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab,
-                                                                   int WY, int32_t *__restrict__ g2, int32_t *__restrict__ cxy,
-                                                                   unsigned long long *__restrict__ scratch, int L,
-                                                                   int *__restrict__ work_counter, int n_items)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
+             const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, uint2 *__restrict__ scratch, int L,
+             int *__restrict__ work_counter)
 {
-    __shared__ int tile_g[WARPS_PER_CTA][32][17];
-    __shared__ int tile_c[WARPS_PER_CTA][32][17];
+    extern __shared__ int xs_smem[];   // per warp: tile_g[32][17], tile_c[32][17], ring[2][RING][32]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * WARPS_PER_CTA + wid;
-    unsigned long long *stack = scratch + (size_t)gwarp * L * 32 + lane;
-    const int X = m.X, Y = m.Y, S = m.max_width;
+    int *wsm = xs_smem + wid * XS_SMEM_INTS_PER_WARP;
+    int (*tile_g)[17] = (int (*)[17])wsm;
+    int (*tile_c)[17] = (int (*)[17])(wsm + 32 * 17);
+    LaneStack st;
+    st.sh = wsm + 2 * 32 * 17 + lane; st.sb = st.sh + RING * 32;
+    st.g = scratch + (size_t)gwarp * L * 32 + lane;
+    const int X = m.X, Y = m.Y;
+    const int n_items = __ldg(n_slices) * WY;
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int z = item / WY, wy = item - z * WY;
+        const int zi = item / WY, wy = item - zi * WY;
+        const int z = __ldg(&slice_list[zi]);
         const int y = wy * 32 + lane;
         const unsigned long long *trow = ytab + ((size_t)z * WY + wy) * X;
+        const int *cols = col_list + (size_t)z * X;
+        const int nc = __ldg(&n_cols[z]);
         int q = -1;
         Top top{0, 0, 0, 0};
-        for (int u = 0; u < X; u++) {
-            unsigned long long e = __ldg(&trow[u]);
-            uint32_t w = (uint32_t)e;
-            int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
-            uint32_t mlo = w & (0xffffffffu >> (31 - lane));
-            uint32_t mhi = w >> lane;
-            int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
-            int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
-            int g1, cy;
-            if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
-            else if (lo >= 0) { g1 = y - lo; cy = lo; }
-            else { g1 = S; cy = INV_Y; }
-            envelope_push(u, g1 * g1, cy, X, q, top, stack);
+        st.base = 0;
+        const uint32_t lomask = 0xffffffffu >> (31 - lane);
+        for (int j0 = 0; j0 < nc; j0 += 4) {
+            // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
+            int uu[4], gg[4], cc[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int j = min(j0 + k, nc - 1);
+                int u = __ldg(&cols[j]);
+                unsigned long long e = __ldg(&trow[u]);
+                uint32_t w = (uint32_t)e;
+                int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
+                uint32_t mlo = w & lomask, mhi = w >> lane;
+                int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
+                int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
+                int g1, cy;
+                if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
+                else { g1 = y - lo; cy = lo; }                                          // a real column always has lo or hi
+                uu[k] = u; gg[k] = g1 * g1; cc[k] = cy;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (j0 + k < nc) envelope_push(uu[k], gg[k], cc[k], X, q, top, st);
         }
         // EDTphase2 backward loop (local_edt_core.h:116-134), emitted through a 32 x 16 tile
         for (int u = X - 1; u >= 0; u--) {
             int d = u - top.s;
-            tile_g[wid][lane][u & 15] = d * d + top.h;
-            tile_c[wid][lane][u & 15] = top.s | (top.cy << 16);
+            tile_g[lane][u & 15] = d * d + top.h;
+            tile_c[lane][u & 15] = top.s | (top.cy << 16);
             if (u == top.t) {
                 q--;
-                if (q >= 0) top = unpack_entry(stack[q * 32]);
+                if (q >= 0) top = st.get(q);
             }
             if ((u & 15) == 0) {
                 __syncwarp();
                 const int col = lane & 15, r0 = lane >> 4;
-#pragma unroll
+                const int xx = u + col;
+                int32_t *pg = g2 + ((size_t)z * Y + wy * 32 + r0) * X + xx;
+                int32_t *pc = cxy + ((size_t)z * Y + wy * 32 + r0) * X + xx;
+#pragma unroll 4
                 for (int i = 0; i < 16; i++) {
                     int r = 2 * i + r0;
-                    int yy = wy * 32 + r, xx = u + col;
-                    if (yy < Y && xx < X) {
-                        size_t o = ((size_t)z * Y + yy) * X + xx;
-                        g2[o] = tile_g[wid][r][col];
-                        cxy[o] = tile_c[wid][r][col];
+                    if (wy * 32 + r < Y && xx < X) {
+                        pg[(size_t)2 * i * X] = tile_g[r][col];
+                        pc[(size_t)2 * i * X] = tile_c[r][col];
                     }
                 }
                 __syncwarp();
@@ -164,16 +248,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_edt_xsweep(LocDev m, con
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2,
-                                                                   const int32_t *__restrict__ cxy,
-                                                                   unsigned long long *__restrict__ scratch, int L,
-                                                                   int *__restrict__ work_counter, int n_items, int XG)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
+             const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
+             int XG)
 {
+    __shared__ int ring[WARPS_PER_CTA][2 * RING * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * WARPS_PER_CTA + wid;
-    unsigned long long *stack = scratch + (size_t)gwarp * L * 32 + lane;
-    const int X = m.X, Y = m.Y, Z = m.Z, S = m.max_width;
-    const size_t slice = (size_t)X * Y;
+    LaneStack st;
+    st.sh = &ring[wid][lane]; st.sb = &ring[wid][RING * 32 + lane];
+    st.g = scratch + (size_t)gwarp * L * 32 + lane;
+    const int X = m.X, Z = m.Z, S = m.max_width;
+    const size_t slice = (size_t)X * m.Y;
+    const int ns = __ldg(n_slices);
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
@@ -182,36 +270,45 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_edt_zsweep(LocDev m, con
         const int y = item / XG, x = (item - y * XG) * 32 + lane;
         const bool valid = x < X;
         const size_t base = (size_t)y * X + (valid ? x : 0);
+        if (ns == 0) {   // no obstacle anywhere: every voxel "sees nothing" (D5)
+            for (int u = 0; u < Z && valid; u++) {
+                m.aux[base + (size_t)u * slice] = S * S;
+                m.coc_aux[base + (size_t)u * slice] = x | (INV_Y << 11) | (u << 22);
+            }
+            continue;
+        }
         int q = -1;
         Top top{0, 0, 0, 0};
-        int k = 0;
-        // forward (EDTphase3, local_edt_core.h:146-168); loads run 4 slices ahead of the dependent scan
-        for (; k + 4 <= Z; k += 4) {
-            int h0 = __ldcs(&g2[base + (size_t)(k + 0) * slice]);
-            int h1 = __ldcs(&g2[base + (size_t)(k + 1) * slice]);
-            int h2 = __ldcs(&g2[base + (size_t)(k + 2) * slice]);
-            int h3 = __ldcs(&g2[base + (size_t)(k + 3) * slice]);
-            envelope_push(k + 0, h0, 0, Z, q, top, stack);
-            envelope_push(k + 1, h1, 0, Z, q, top, stack);
-            envelope_push(k + 2, h2, 0, Z, q, top, stack);
-            envelope_push(k + 3, h3, 0, Z, q, top, stack);
+        st.base = 0;
+        // forward (EDTphase3, local_edt_core.h:146-168) over the slices that hold obstacles; loads run ahead of the scan
+        int j = 0;
+        for (; j + 4 <= ns; j += 4) {
+            int k0 = __ldg(&slice_list[j]), k1 = __ldg(&slice_list[j + 1]), k2 = __ldg(&slice_list[j + 2]), k3 = __ldg(&slice_list[j + 3]);
+            int h0 = __ldcs(&g2[base + (size_t)k0 * slice]);
+            int h1 = __ldcs(&g2[base + (size_t)k1 * slice]);
+            int h2 = __ldcs(&g2[base + (size_t)k2 * slice]);
+            int h3 = __ldcs(&g2[base + (size_t)k3 * slice]);
+            envelope_push(k0, h0, 0, Z, q, top, st);
+            envelope_push(k1, h1, 0, Z, q, top, st);
+            envelope_push(k2, h2, 0, Z, q, top, st);
+            envelope_push(k3, h3, 0, Z, q, top, st);
         }
-        for (; k < Z; k++) envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, stack);
+        for (; j < ns; j++) {
+            int k = __ldg(&slice_list[j]);
+            envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
+        }
         // backward (local_edt_core.h:169-192)
+        int c = __ldg(&cxy[base + (size_t)top.s * slice]);
         for (int u = Z - 1; u >= 0; u--) {
             int d = u - top.s;
-            int dist = d * d + top.h;
-            int c = __ldg(&cxy[base + (size_t)top.s * slice]);
-            int cx = c & 0xffff, cy = c >> 16;
-            int coc = (cy < S) ? (cx | (cy << 11) | (top.s << 22)) : (x | (INV_Y << 11) | (u << 22));
             if (valid) {
                 size_t o = base + (size_t)u * slice;
-                m.aux[o] = dist;
-                m.coc_aux[o] = coc;
+                __stcs(&m.aux[o], d * d + top.h);
+                __stcs(&m.coc_aux[o], (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22));
             }
             if (u == top.t) {
                 q--;
-                if (q >= 0) top = unpack_entry(stack[q * 32]);
+                if (q >= 0) { top = st.get(q); c = __ldg(&cxy[base + (size_t)top.s * slice]); }
             }
         }
     }
@@ -226,6 +323,8 @@ int gie_edt_prepare(gie_locmap *lm)
     GIE_CUDA_CHECK(cudaMalloc(&lm->ytab, (size_t)m.Z * WY * m.X * 8));
     GIE_CUDA_CHECK(cudaMalloc(&lm->g2, (size_t)m.N * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->cxy, (size_t)m.N * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&lm->col_list, (size_t)m.Z * m.X * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&lm->edt_meta, (size_t)(2 * m.Z + 8) * 4));   // n_cols[Z], slice_list[Z], n_slices
     int L = m.X > m.Z ? m.X : m.Z;
     int n_items = max(m.Z * WY, m.Y * ((m.X + 31) / 32));
     int ctas = lm->num_sms * 4;
@@ -235,6 +334,7 @@ int gie_edt_prepare(gie_locmap *lm)
     lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
     GIE_CUDA_CHECK(cudaMalloc(&lm->stack_scratch, lm->stack_scratch_entries * 8));
     GIE_CUDA_CHECK(cudaMalloc(&lm->work_counters, 4 * sizeof(int)));
+    GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM_BYTES));
     return GIE_OK;
 }
 
@@ -243,23 +343,26 @@ int gie_launch_batch_edt(gie_locmap *lm)
     const LocDev &m = lm->d;
     const int WY = (m.Y + 31) / 32, XG = (m.X + 31) / 32;
     const int L = m.X > m.Z ? m.X : m.Z;
+    int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     {
         StageTimer t(lm, GIE_ST_EDT_PACK);
-        dim3 grid((m.X + 127) / 128, m.Z);
-        k_edt_ycols<<<grid, 128, 0, lm->stream>>>(m, lm->ytab, WY);
+        k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
+        k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_X);
-        k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->g2, lm->cxy, lm->stack_scratch,
-                                                                          L, lm->work_counters + 0, m.Z * WY);
+        k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                                          lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L,
+                                                                          lm->work_counters + 0);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_Z);
-        k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, lm->stack_scratch, L,
-                                                                          lm->work_counters + 1, m.Y * XG, XG);
+        k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices,
+                                                                          (uint2 *)lm->stack_scratch, L, lm->work_counters + 1,
+                                                                          m.Y * XG, XG);
     }
-    lm->launches += 3;
+    lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

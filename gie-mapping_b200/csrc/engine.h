@@ -14,6 +14,8 @@ struct gie_locmap {
     unsigned long long *ytab = nullptr;   // [Z][ceil(Y/32)][X] (mask word, lo_prev, hi_next)
     int32_t *g2 = nullptr;                // [Z][Y][X] plane dist_sq after the x sweep
     int32_t *cxy = nullptr;               // [Z][Y][X] cocx | cocy << 16
+    int *col_list = nullptr;              // [Z][X] columns of each slice that hold an obstacle (ascending)
+    int *edt_meta = nullptr;              // n_cols[Z], slice_list[Z], n_slices
     unsigned long long *stack_scratch = nullptr;
     size_t stack_scratch_entries = 0;
     int edt_ctas = 0;                     // persistent grid of the sweep kernels
