@@ -11,6 +11,7 @@
 // ONE probe per block; the merge kernel allocates a block the first time it meets an observed voxel whose block is
 // missing (a fresh block is all-UNKNOWN, so voxels of that block merged earlier with "no block" are already right).
 #include "engine.h"
+#include <algorithm>
 
 namespace {
 
@@ -67,63 +68,85 @@ __device__ __forceinline__ void set_occ_val(uint8_t &occ, int8_t &type, float va
     type = (occ > thresh) ? GIE_VOX_OCCUPIED : GIE_VOX_FREE;
 }
 
-// updateHashOGMWithPntCld / updateHashOGMWithSensor, one thread per voxel, x fastest
-template <bool PNTCLD>
+// updateHashOGMWithPntCld / updateHashOGMWithSensor.  Each thread owns VEC consecutive voxels along x (vector loads /
+// stores on the dense arrays); a grid-stride loop over a grid sized to the SM count keeps CTAs resident.
+template <bool PNTCLD, int VEC>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, z = blockIdx.z;
-    const bool valid = x < m.X;
-    int3 c = make_int3(valid ? x : 0, y, z);
-    int id = gie_lidx(m, c);
-    int count = 0;
-    int8_t inst = GIE_VOX_UNKNOWN;
-    if (valid) {
-        inst = m.inst_type[id];
-        if (PNTCLD) {
-            count = m.ray_count[id];
-            if (count != 0) m.ray_count[id] = 0;
-        }
-        if (inst != GIE_VOX_UNKNOWN) m.inst_type[id] = GIE_VOX_UNKNOWN;
-    }
-    bool observed = valid && (PNTCLD ? (count != 0) : (inst == GIE_VOX_OCCUPIED || inst == GIE_VOX_FREE));
-    int3 glb = c + m.pvt;
-    int ti = gie_tab_index(h, glb);
-    int blk = __ldcg(&h.btab[ti]);
-    // warp-aggregated allocation: one lane per distinct missing block inserts, the others take its result
-    {
-        const bool need = blk < 0 && observed;
-        const int lane = threadIdx.x & 31;
-        unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
-        int leader = __ffs(grp) - 1;
-        int res = -1;
-        if (need && lane == leader) {
-            res = hash_insert(h, gie_vb_key(glb));
-            if (res >= 0) h.btab[ti] = res;
-        }
-        res = __shfl_sync(0xffffffffu, res, leader);
-        if (need) blk = res;
-    }
-    if (!valid) return;
-    if (blk < 0) { m.glb_type[id] = GIE_VOX_UNKNOWN; return; }
-    size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
-    int8_t type = h.vox_type[vi];
-    if (observed) {
-        uint8_t occ = h.occ_val[vi];
-        if (PNTCLD) {
-            if (count > 0) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
-            else {
-                float p = fminf(1.f, __fdiv_rn((float)(-count), 10.f));
-                set_occ_val(occ, type, 0.f, p, m.thresh);
-            }
+    const int nq = m.N / VEC;                       // X % VEC == 0, so a group never straddles a row
+    const int nq_pad = (nq + 31) & ~31;             // whole warps run the collective below
+    const int lane = threadIdx.x & 31;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq_pad; q += gridDim.x * blockDim.x) {
+        const bool valid = q < nq;
+        const int id0 = valid ? q * VEC : 0;
+        const int x0 = id0 % m.X, yz = id0 / m.X;
+        const int y = yz % m.Y, z = yz / m.Y;
+        int cnt[VEC];
+        int8_t inst[VEC], out_type[VEC];
+        if (VEC == 4) {
+            char4 i4 = valid ? *reinterpret_cast<const char4 *>(m.inst_type + id0) : make_char4(0, 0, 0, 0);
+            inst[0] = i4.x; inst[1] = i4.y; inst[2] = i4.z; inst[3] = i4.w;
+            int4 c4 = make_int4(0, 0, 0, 0);
+            if (PNTCLD && valid) c4 = *reinterpret_cast<const int4 *>(m.ray_count + id0);
+            cnt[0] = c4.x; cnt[1] = c4.y; cnt[2] = c4.z; cnt[3] = c4.w;
         } else {
-            if (inst == GIE_VOX_OCCUPIED) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
-            else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
+            inst[0] = valid ? m.inst_type[id0] : 0;
+            cnt[0] = (PNTCLD && valid) ? m.ray_count[id0] : 0;
         }
-        h.occ_val[vi] = occ;
-        h.vox_type[vi] = type;
+        bool any_cnt = false, any_inst = false;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            any_cnt |= cnt[k] != 0; any_inst |= inst[k] != GIE_VOX_UNKNOWN;
+            const bool observed = valid && (PNTCLD ? (cnt[k] != 0) : (inst[k] == GIE_VOX_OCCUPIED || inst[k] == GIE_VOX_FREE));
+            const int3 glb = make_int3(x0 + k, y, z) + m.pvt;
+            const int ti = gie_tab_index(h, glb);
+            int blk = __ldcg(&h.btab[ti]);
+            // warp-aggregated allocation: one lane per distinct missing block inserts, the others take its result
+            {
+                const bool need = blk < 0 && observed;
+                unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
+                int leader = __ffs(grp) - 1;
+                int res = -1;
+                if (need && lane == leader) {
+                    res = hash_insert(h, gie_vb_key(glb));
+                    if (res >= 0) h.btab[ti] = res;
+                }
+                res = __shfl_sync(0xffffffffu, res, leader);
+                if (need) blk = res;
+            }
+            int8_t type = GIE_VOX_UNKNOWN;
+            if (valid && blk >= 0) {
+                size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
+                type = h.vox_type[vi];
+                if (observed) {
+                    uint8_t occ = h.occ_val[vi];
+                    if (PNTCLD) {
+                        if (cnt[k] > 0) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
+                        else {
+                            float p = fminf(1.f, __fdiv_rn((float)(-cnt[k]), 10.f));
+                            set_occ_val(occ, type, 0.f, p, m.thresh);
+                        }
+                    } else {
+                        if (inst[k] == GIE_VOX_OCCUPIED) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
+                        else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
+                    }
+                    h.occ_val[vi] = occ;
+                    h.vox_type[vi] = type;
+                }
+            }
+            out_type[k] = type;
+        }
+        if (!valid) continue;
+        if (VEC == 4) {
+            if (any_cnt) *reinterpret_cast<int4 *>(m.ray_count + id0) = make_int4(0, 0, 0, 0);
+            if (any_inst) *reinterpret_cast<char4 *>(m.inst_type + id0) = make_char4(0, 0, 0, 0);
+            *reinterpret_cast<char4 *>(m.glb_type + id0) = make_char4(out_type[0], out_type[1], out_type[2], out_type[3]);
+        } else {
+            if (any_cnt) m.ray_count[id0] = 0;
+            if (any_inst) m.inst_type[id0] = GIE_VOX_UNKNOWN;
+            m.glb_type[id0] = out_type[0];
+        }
     }
-    m.glb_type[id] = type;
 }
 
 __global__ void k_export(HashDev h, int nblocks, gie_glbvoxel *out)
@@ -157,10 +180,16 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct)
 {
     gie_locmap *lm = hm->lm;
     StageTimer t(lm, GIE_ST_HASH_MERGE);
-    dim3 block(256), grid((lm->d.X + 255) / 256, lm->d.Y, lm->d.Z);
-    if (lm->d.X <= 128) { block = dim3(128); grid.x = (lm->d.X + 127) / 128; }
-    if (input_pntcld) k_merge_ogm<true><<<grid, block, 0, lm->stream>>>(lm->d, hm->d, map_ct);
-    else k_merge_ogm<false><<<grid, block, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+    const int vec = (lm->d.X % 4 == 0) ? 4 : 1;
+    long long groups = (long long)lm->d.N / vec;
+    int grid = (int)std::min<long long>((groups + 255) / 256, (long long)lm->num_sms * 16);
+    if (vec == 4) {
+        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+    } else {
+        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+    }
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;

@@ -61,115 +61,150 @@ __device__ __forceinline__ bool q_push(T *q, int *cnt, int cap, T v, int *status
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MarkLimitedObserve (unify_helper.cuh:201-273), one thread per voxel, x fastest.  D4: UNKNOWN voxels get their batch
-// values instead of keeping stale memory.
+// MarkLimitedObserve (unify_helper.cuh:201-273).  Each thread owns VEC consecutive voxels along x (vector loads/stores),
+// grid-stride over a grid sized to the SM count.  D4: UNKNOWN voxels get their batch values instead of stale memory.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_mark(LocDev m, HashDev h)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, z = blockIdx.z;
-    if (x >= m.X) return;
-    int3 c = make_int3(x, y, z);
-    int id = gie_lidx(m, c);
-    int8_t type = m.glb_type[id];
-    int3 coc_new = gie_id2wr((uint32_t)m.coc_aux[id]);   // same 11/11/10 packing, local coords
-    int dist_new = m.aux[id];
-    int aux = dist_new;
-    uint32_t pid = 0;
-    int pdist = 0;
+    const int nq = m.N / VEC;
     const int mw = m.max_width;
-    bool see_nothing = coc_new.x > mw || coc_new.y > mw || coc_new.z > mw;   // invalid_coc_buf, voxmap_utils.cuh:174-179
-    if (see_nothing) { pdist = GIE_EMPTY_VALUE; pid = 0xffffffffu; aux = GIE_EMPTY_VALUE; }
-    if (type != GIE_VOX_UNKNOWN) {
-        int3 glb = c + m.pvt;
-        int blk = gie_block_of(h, glb);
-        if (blk >= 0) {   // a known voxel always has a block
-            size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
-            int dist_old = h.dist_sq[vi];
-            int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
-            if (dist_new > dist_old && !gie_inside_loc(m, coc_buf_old)) { coc_new = coc_buf_old; aux = dist_old; }
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int id0 = q * VEC;
+        const int x0 = id0 % m.X, yz = id0 / m.X;
+        const int y = yz % m.Y, z = yz / m.Y;
+        int8_t type[VEC]; int dist[VEC], cocv[VEC];
+        unsigned long long pr[VEC];
+        if (VEC == 4) {
+            char4 t4 = *reinterpret_cast<const char4 *>(m.glb_type + id0);
+            int4 a4 = *reinterpret_cast<const int4 *>(m.aux + id0);
+            int4 c4 = *reinterpret_cast<const int4 *>(m.coc_aux + id0);
+            type[0] = t4.x; type[1] = t4.y; type[2] = t4.z; type[3] = t4.w;
+            dist[0] = a4.x; dist[1] = a4.y; dist[2] = a4.z; dist[3] = a4.w;
+            cocv[0] = c4.x; cocv[1] = c4.y; cocv[2] = c4.z; cocv[3] = c4.w;
+        } else { type[0] = m.glb_type[id0]; dist[0] = m.aux[id0]; cocv[0] = m.coc_aux[id0]; }
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            const int3 c = make_int3(x0 + k, y, z);
+            int3 coc_new = gie_id2wr((uint32_t)cocv[k]);   // same 11/11/10 packing, local coords
+            const int dist_new = dist[k];
+            int aux = dist_new;
+            uint32_t pid = 0;
+            int pdist = 0;
+            const bool see_nothing = coc_new.x > mw || coc_new.y > mw || coc_new.z > mw;   // invalid_coc_buf, voxmap_utils.cuh:174-179
+            if (see_nothing) { pdist = GIE_EMPTY_VALUE; pid = 0xffffffffu; aux = GIE_EMPTY_VALUE; }
+            if (type[k] != GIE_VOX_UNKNOWN) {
+                int3 glb = c + m.pvt;
+                int blk = gie_block_of(h, glb);
+                if (blk >= 0) {   // a known voxel always has a block
+                    size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
+                    int dist_old = h.dist_sq[vi];
+                    int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
+                    if (dist_new > dist_old && !gie_inside_loc(m, coc_buf_old)) { coc_new = coc_buf_old; aux = dist_old; }
+                }
+            }
+            int3 wr = coc_new + m.pvt - m.upvt;
+            if (!gie_inside_wr(wr)) { pdist = GIE_EMPTY_VALUE; aux = GIE_EMPTY_VALUE; if (!see_nothing) pid = GIE_INVALID_ID_STALE; }
+            else { pdist = aux; pid = gie_wr2id(wr); }
+            pr[k] = gie_mk_pair(pdist, pid);
+            if (aux != dist_new) m.aux[id0 + k] = aux;
         }
+        if (VEC == 4) {
+            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(m.pair + id0);
+            dst[0] = make_ulonglong2(pr[0], pr[1]);
+            dst[1] = make_ulonglong2(pr[2], pr[3]);
+        } else m.pair[id0] = pr[0];
     }
-    int3 wr = coc_new + m.pvt - m.upvt;
-    if (!gie_inside_wr(wr)) { pdist = GIE_EMPTY_VALUE; aux = GIE_EMPTY_VALUE; if (!see_nothing) pid = GIE_INVALID_ID_STALE; }
-    else { pdist = aux; pid = gie_wr2id(wr); }
-    m.pair[id] = gie_mk_pair(pdist, pid);
-    if (aux != dist_new) m.aux[id] = aux;
 }
 
 // obtainFrontiers (unify_helper.cuh:275-446).  pair[] is read-only here: a lowered own pair (frontier C seed) is
 // deferred into cseed_key and applied by the wave kernel, which removes the reference's _g/_coc_idx backup arrays.
+template <int VEC>
 __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, z = blockIdx.z;
-    if (x >= m.X) return;
-    int3 c = make_int3(x, y, z);
-    int id = gie_lidx(m, c);
-    int8_t type = m.glb_type[id];
-    int wl = GIE_EMPTY_VALUE;
-    if (type != GIE_VOX_UNKNOWN) {
-        unsigned long long pr = m.pair[id];
-        int3 cur_wr = gie_id2wr(gie_pair_id(pr));
-        int3 cur_coc_glb = cur_wr + m.upvt;
-        int3 cur_coc_buf = cur_coc_glb - m.pvt;
-        int cur_dist = gie_pair_dist(pr);
-        if (gie_inside_loc(m, cur_coc_buf)) {
-            bool nbr_unknown = false, lowered = false;
-            unsigned long long new_key = 0;
+    const int nq = m.N / VEC;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int id0 = q * VEC;
+        const int x0 = id0 % m.X, yz = id0 / m.X;
+        const int y = yz % m.Y, z = yz / m.Y;
+        int8_t types[VEC]; int wls[VEC];
+        if (VEC == 4) {
+            char4 t4 = *reinterpret_cast<const char4 *>(m.glb_type + id0);
+            types[0] = t4.x; types[1] = t4.y; types[2] = t4.z; types[3] = t4.w;
+        } else types[0] = m.glb_type[id0];
 #pragma unroll
-            for (int d = 0; d < 6; d++) {
-                int3 nb = c + DIRS6[d];
-                if (gie_inside_loc(m, nb)) {
-                    int nid = gie_lidx(m, nb);
-                    if (m.glb_type[nid] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
-                    int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
-                    int3 ncb = nwr + m.upvt - m.pvt;
-                    if (!gie_inside_loc(m, ncb) && gie_inside_wr(nwr)) {
-                        int d2 = sqd3(ncb, c);
-                        if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
-                    }
-                } else {
-                    int3 nglb = nb + m.pvt;
-                    size_t vi;
-                    if (!vox_ref(h, nglb, vi)) { nbr_unknown = true; continue; }
-                    if (h.vox_type[vi] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
-                    int ndist = h.dist_sq[vi];
-                    if (gie_invalid_dist_glb(ndist)) continue;
-                    int3 ncoc = gie_unpack_coc(h.coc_glb[vi]);
-                    if (gie_invalid_coc_glb(ncoc)) continue;
-                    int3 nwr = ncoc - m.upvt;
-                    bool n_valid = gie_inside_wr(nwr);
-                    int3 ncb = ncoc - m.pvt;
-                    bool n_local = gie_inside_loc(m, ncb);
-                    if (!n_local && n_valid) {
-                        int d2 = sqd3(ncb, c);
-                        if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
-                    }
-                    if (m.fast) continue;
-                    int c2n = sqd3(nb, cur_coc_buf);
-                    if (c2n < ndist) {                       // lower-out seed (frontier B)
-                        h.wave_layer[vi] = 1; h.update_ct[vi] = map_ct;
-                        h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
-                        q_push(w.qB[0], &w.cnt[C_B0], w.cap, pack_glb(nglb), h.status);
-                    } else if (c2n > ndist && n_local) {     // raise-out seed (frontier A)
-                        if (m.glb_type[gie_lidx(m, ncb)] != GIE_VOX_OCCUPIED) {
-                            h.dist_sq[vi] = c2n; h.coc_glb[vi] = gie_pack_coc(cur_coc_glb); h.wave_layer[vi] = -map_ct;
-                            h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
-                            q_push(w.qA[0], &w.cnt[C_A0], w.cap, pack_glb(nglb), h.status);
+        for (int kk = 0; kk < VEC; kk++) {
+            const int3 c = make_int3(x0 + kk, y, z);
+            const int id = id0 + kk;
+            const int8_t type = types[kk];
+            int wl = GIE_EMPTY_VALUE;
+            if (type != GIE_VOX_UNKNOWN) {
+                unsigned long long pr = m.pair[id];
+                int3 cur_wr = gie_id2wr(gie_pair_id(pr));
+                int3 cur_coc_glb = cur_wr + m.upvt;
+                int3 cur_coc_buf = cur_coc_glb - m.pvt;
+                int cur_dist = gie_pair_dist(pr);
+                if (gie_inside_loc(m, cur_coc_buf)) {
+                    bool nbr_unknown = false, lowered = false;
+                    unsigned long long new_key = 0;
+    #pragma unroll
+                    for (int d = 0; d < 6; d++) {
+                        int3 nb = c + DIRS6[d];
+                        if (gie_inside_loc(m, nb)) {
+                            int nid = gie_lidx(m, nb);
+                            if (m.glb_type[nid] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
+                            int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
+                            int3 ncb = nwr + m.upvt - m.pvt;
+                            if (!gie_inside_loc(m, ncb) && gie_inside_wr(nwr)) {
+                                int d2 = sqd3(ncb, c);
+                                if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
+                            }
+                        } else {
+                            int3 nglb = nb + m.pvt;
+                            size_t vi;
+                            if (!vox_ref(h, nglb, vi)) { nbr_unknown = true; continue; }
+                            if (h.vox_type[vi] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
+                            int ndist = h.dist_sq[vi];
+                            if (gie_invalid_dist_glb(ndist)) continue;
+                            int3 ncoc = gie_unpack_coc(h.coc_glb[vi]);
+                            if (gie_invalid_coc_glb(ncoc)) continue;
+                            int3 nwr = ncoc - m.upvt;
+                            bool n_valid = gie_inside_wr(nwr);
+                            int3 ncb = ncoc - m.pvt;
+                            bool n_local = gie_inside_loc(m, ncb);
+                            if (!n_local && n_valid) {
+                                int d2 = sqd3(ncb, c);
+                                if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
+                            }
+                            if (m.fast) continue;
+                            int c2n = sqd3(nb, cur_coc_buf);
+                            if (c2n < ndist) {                       // lower-out seed (frontier B)
+                                h.wave_layer[vi] = 1; h.update_ct[vi] = map_ct;
+                                h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
+                                q_push(w.qB[0], &w.cnt[C_B0], w.cap, pack_glb(nglb), h.status);
+                            } else if (c2n > ndist && n_local) {     // raise-out seed (frontier A)
+                                if (m.glb_type[gie_lidx(m, ncb)] != GIE_VOX_OCCUPIED) {
+                                    h.dist_sq[vi] = c2n; h.coc_glb[vi] = gie_pack_coc(cur_coc_glb); h.wave_layer[vi] = -map_ct;
+                                    h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
+                                    q_push(w.qA[0], &w.cnt[C_A0], w.cap, pack_glb(nglb), h.status);
+                                }
+                            }
                         }
                     }
+                    if (lowered) {                                   // lower-in seed (frontier C)
+                        wl = 1;
+                        int i = atomicAdd(&w.cnt[C_C0], 1);
+                        if (i < w.cap) { w.qC[0][i] = id; w.cseed_key[i] = new_key; }
+                        else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
+                    }
+                    if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
                 }
             }
-            if (lowered) {                                   // lower-in seed (frontier C)
-                wl = 1;
-                int i = atomicAdd(&w.cnt[C_C0], 1);
-                if (i < w.cap) { w.qC[0][i] = id; w.cseed_key[i] = new_key; }
-                else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
-            }
-            if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
+
+            wls[kk] = wl;
         }
+        if (VEC == 4) *reinterpret_cast<int4 *>(m.wave_layer + id0) = make_int4(wls[0], wls[1], wls[2], wls[3]);
+        else m.wave_layer[id0] = wls[0];
     }
-    m.wave_layer[id] = wl;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -406,31 +441,43 @@ __global__ void __launch_bounds__(256) k_waves(LocDev m, HashDev h, WaveDev w, i
 }
 
 // UpdateHashBatch (unify_helper.cuh:448-523)
+template <int VEC>
 __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y, z = blockIdx.z;
-    if (x >= m.X) return;
-    int3 c = make_int3(x, y, z);
-    int id = gie_lidx(m, c);
-    int8_t type = m.glb_type[id];
-    if (type == GIE_VOX_UNKNOWN) return;
-    unsigned long long pr = m.pair[id];
-    int dist = gie_pair_dist(pr);
-    uint32_t pid = gie_pair_id(pr);
-    if (dist == GIE_EMPTY_VALUE) {
-        if (pid == 0xffffffffu) m.edt[id] = (float)m.max_loc_dist_sq;
-        return;
+    const int nq = m.N / VEC;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+        const int id0 = q * VEC;
+        int8_t types[VEC];
+        if (VEC == 4) {
+            char4 t4 = *reinterpret_cast<const char4 *>(m.glb_type + id0);
+            types[0] = t4.x; types[1] = t4.y; types[2] = t4.z; types[3] = t4.w;
+            if ((t4.x | t4.y | t4.z | t4.w) == 0) continue;
+        } else types[0] = m.glb_type[id0];
+        const int x0 = id0 % m.X, yz = id0 / m.X;
+        const int y = yz % m.Y, z = yz / m.Y;
+#pragma unroll
+        for (int k = 0; k < VEC; k++) {
+            const int8_t type = types[k];
+            if (type == GIE_VOX_UNKNOWN) continue;
+            const int id = id0 + k;
+            unsigned long long pr = m.pair[id];
+            int dist = gie_pair_dist(pr);
+            uint32_t pid = gie_pair_id(pr);
+            if (dist == GIE_EMPTY_VALUE) {
+                if (pid == 0xffffffffu) m.edt[id] = (float)m.max_loc_dist_sq;
+                continue;
+            }
+            int3 glb = make_int3(x0 + k, y, z) + m.pvt;
+            int blk = gie_block_of(h, glb);
+            if (blk < 0) continue;
+            size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
+            h.coc_glb[vi] = gie_pack_coc(gie_id2wr(pid) + m.upvt);
+            h.dist_sq[vi] = dist;
+            m.edt[id] = sqrtf((float)dist);
+            h.pair[vi] = pr;
+            if (type == GIE_VOX_FNT) h.vox_type[vi] = GIE_VOX_FNT;
+        }
     }
-    int3 glb = c + m.pvt;
-    int blk = gie_block_of(h, glb);
-    if (blk < 0) return;
-    size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
-    h.coc_glb[vi] = gie_pack_coc(gie_id2wr(pid) + m.upvt);
-    h.dist_sq[vi] = dist;
-    m.edt[id] = sqrtf((float)dist);
-    h.pair[vi] = pr;
-    if (type == GIE_VOX_FNT) h.vox_type[vi] = GIE_VOX_FNT;
 }
 
 __global__ void k_wave_stats(WaveDev w, long long *out)
@@ -486,14 +533,21 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct)
     gie_locmap *lm = hm->lm;
     const LocDev &m = lm->d;
     WaveDev w = make_wave_dev(hm);
-    dim3 block(256), grid((m.X + 255) / 256, m.Y, m.Z);
-    if (m.X <= 128) { block = dim3(128); grid.x = (m.X + 127) / 128; }
+    const int vec = (m.X % 4 == 0) ? 4 : 1;
+    long long groups = (long long)m.N / vec;
+    long long want = (groups + 255) / 256, cap = (long long)lm->num_sms * 16;
+    const int grid = (int)(want < cap ? want : cap);
     {
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->counters, 0, C_COUNT * sizeof(int), lm->stream));
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, sizeof(unsigned int), lm->stream));
-        k_mark<<<grid, block, 0, lm->stream>>>(m, hm->d);
-        k_frontiers<<<grid, block, 0, lm->stream>>>(m, hm->d, w, map_ct);
+        if (vec == 4) {
+            k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+            k_frontiers<4><<<grid, 256, 0, lm->stream>>>(m, hm->d, w, map_ct);
+        } else {
+            k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+            k_frontiers<1><<<grid, 256, 0, lm->stream>>>(m, hm->d, w, map_ct);
+        }
     }
     {
         StageTimer t(lm, GIE_ST_WAVES);
@@ -503,7 +557,8 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct)
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        k_commit<<<grid, block, 0, lm->stream>>>(m, hm->d);
+        if (vec == 4) k_commit<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+        else k_commit<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
     }
     k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->stats_host);
     lm->launches += 5;
