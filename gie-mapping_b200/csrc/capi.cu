@@ -145,36 +145,59 @@ int gie_set_stream(gie_locmap *lm, void *cuda_stream)
     return GIE_OK;
 }
 
-int gie_locmap_set_pose(gie_locmap *lm, const float q[4], const float t[3])
+int gie_make_projection(const float q[4], const float t[3], float L2G[12], float G2L[12])
 {
-    if (!lm || !q || !t) return GIE_ERR_INVALID_ARG;
-    LocDev &m = lm->d;
+    if (!q || !t || !L2G || !G2L) return GIE_ERR_INVALID_ARG;
     // cudaMat::SE3 quaternion constructor (include/cuda_toolkit/se3.cuh:47-75), float, evaluated as written
     volatile float qw = q[0], qx = q[1], qy = q[2], qz = q[3];
     float x = 2 * qx, y = 2 * qy, z = 2 * qz;
     float wx = x * qw, wy = y * qw, wz = z * qw;
     float xx = x * qx, xy = y * qx, xz = z * qx, yy = y * qy, yz = z * qy, zz = z * qz;
-    float *d = m.L2G;
+    float *d = L2G;
     d[0] = 1 - (yy + zz); d[1] = xy - wz; d[2] = xz + wy;
     d[4] = xy + wz; d[5] = 1 - (xx + zz); d[6] = yz - wx;
     d[8] = xz - wy; d[9] = yz + wx; d[10] = 1 - (xx + yy);
     d[3] = t[0]; d[7] = t[1]; d[11] = t[2];
     // SE3::inv (se3.cuh:89-105)
-    float *r = m.G2L;
+    float *r = G2L;
     r[0] = d[0]; r[1] = d[4]; r[2] = d[8];
     r[4] = d[1]; r[5] = d[5]; r[6] = d[9];
     r[8] = d[2]; r[9] = d[6]; r[10] = d[10];
     r[3] = -d[0] * d[3] - d[4] * d[7] - d[8] * d[11];
     r[7] = -d[1] * d[3] - d[5] * d[7] - d[9] * d[11];
     r[11] = -d[2] * d[3] - d[6] * d[7] - d[10] * d[11];
-    m.origin = make_float3(t[0], t[1], t[2]);
+    return GIE_OK;
+}
+
+int gie_locmap_set_projection(gie_locmap *lm, const float L2G[12], const float G2L[12], const float origin[3])
+{
+    if (!lm || !L2G || !G2L || !origin) return GIE_ERR_INVALID_ARG;
+    memcpy(lm->d.L2G, L2G, sizeof(float) * 12);
+    memcpy(lm->d.G2L, G2L, sizeof(float) * 12);
+    lm->d.origin = make_float3(origin[0], origin[1], origin[2]);
+    return GIE_OK;
+}
+
+int gie_locmap_calculate_pivots(gie_locmap *lm, const float center[3])
+{
+    if (!lm || !center) return GIE_ERR_INVALID_ARG;
+    LocDev &m = lm->d;
     // LocMap::calculate_pivot_origin / calculate_update_pivot (local_batch.h:128-166)
-    int3 c = make_int3((int)floorf(t[0] / m.w + 0.5f), (int)floorf(t[1] / m.w + 0.5f), (int)floorf(t[2] / m.w + 0.5f));
+    int3 c = make_int3((int)floorf(center[0] / m.w + 0.5f), (int)floorf(center[1] / m.w + 0.5f), (int)floorf(center[2] / m.w + 0.5f));
     m.pvt = make_int3(c.x - m.X / 2, c.y - m.Y / 2, c.z - m.Z / 2);
     m.upvt = make_int3(c.x - GIE_WR_X / 2, c.y - GIE_WR_Y / 2, c.z - GIE_WR_Z / 2);
     lm->msg_origin = make_float3((float)m.pvt.x * m.w, (float)m.pvt.y * m.w, (float)m.pvt.z * m.w);
     if (lm->hm) return gie_hash_begin_frame(lm->hm);
     return GIE_OK;
+}
+
+int gie_locmap_set_pose(gie_locmap *lm, const float q[4], const float t[3])
+{
+    if (!lm || !q || !t) return GIE_ERR_INVALID_ARG;
+    float L2G[12], G2L[12];
+    gie_make_projection(q, t, L2G, G2L);
+    gie_locmap_set_projection(lm, L2G, G2L, t);
+    return gie_locmap_calculate_pivots(lm, t);
 }
 
 int gie_locmap_get_pivots(const gie_locmap *lm, int out6[6], float origin3[3])

@@ -80,6 +80,15 @@ int gie_set_stream(gie_locmap *lm, void *cuda_stream);
 /* trans2proj (include/cuda_toolkit/projection.h:15-33) + LocMap::calculate_pivot_origin / calculate_update_pivot
  * (local_batch.h:128-166), as called at volumetric_mapper.cpp:144-155.  q = (w,x,y,z) body->world, t = translation. */
 int gie_locmap_set_pose(gie_locmap *lm, const float q_wxyz[4], const float t_xyz[3]);
+/* The same three steps as separate calls, for callers that keep the reference's call order (volumetric_mapper.cpp:144-155,
+ * where proj.origin.z may be overridden by ugv_height before the pivots are computed):
+ *   gie_make_projection        = trans2proj: cudaMat::SE3(qw,qx,qy,qz,tx,ty,tz) and its inverse (se3.cuh:47-75,89-105),
+ *                                row-major 3x4 [R|t]
+ *   gie_locmap_set_projection  = the `Projection proj` the reference passes by value to every localOGMKernels
+ *   gie_locmap_calculate_pivots= LocMap::calculate_pivot_origin + calculate_update_pivot (local_batch.h:128-166) */
+int gie_make_projection(const float q_wxyz[4], const float t_xyz[3], float L2G[12], float G2L[12]);
+int gie_locmap_set_projection(gie_locmap *lm, const float L2G[12], const float G2L[12], const float origin[3]);
+int gie_locmap_calculate_pivots(gie_locmap *lm, const float map_center[3]);
 /* out6 = {_pvt.xyz, _update_pvt.xyz}; origin3 = _msg_origin */
 int gie_locmap_get_pivots(const gie_locmap *lm, int out6[6], float origin3[3]);
 /* LocMap::copy_ogm_2_host / copy_edt_2_host / convertCostMap (local_batch.h:370-391) */

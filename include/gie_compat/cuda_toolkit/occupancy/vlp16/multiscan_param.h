@@ -1,0 +1,3 @@
+#pragma once
+#include <vector_types.h>
+#include "cuda_toolkit/occupancy/sensor_params.h"

@@ -1,0 +1,2 @@
+#pragma once
+#include "kernel/ogm_interfaces.h"
