@@ -56,44 +56,44 @@ ALGO_BYTES = {
 
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index):
+    """Samples SM clock and clock-event reasons DURING the timed region, in-process through NVML (a polling `nvidia-smi`
+    subprocess stalls host<->device synchronisation for tens of ms per query, which lands in the e2e number)."""
+
+    def __init__(self, index, period_s=0.02):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
+        self.index, self.period = index, period_s
+        self.sm, self.reasons = [], set()
+        self.sm_max = None
         self.stop_flag = False
-        self.proc = None
+        self.active = False     # samples are kept only while a timed region is open
 
     def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                if self.stop_flag:
-                    break
-                self.samples.append([p.strip() for p in line.split(",")])
-        except Exception:
-            pass
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+            while not self.stop_flag:
+                if self.active:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:   # no NVML: report nothing rather than a made-up clock
+            self.error = repr(e)
 
     def stop(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-                for n, v in zip(names, s[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "how": "NVML, 20 ms period, timed regions only"}
 
 
 def measured_peak():
@@ -214,6 +214,7 @@ def main():
         barrier()
         l0 = mp.loc_map.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.active = True
         e0.record(stream)
         for k in range(args.warmup, nframes):
             if device_resident:
@@ -227,6 +228,7 @@ def main():
                 result[0] = st["fC"]
         e1.record(stream)
         barrier()
+        sampler.active = False
         ms = e0.elapsed_time(e1) / args.steps
         launches = mp.loc_map.launch_count() - l0
         if world > 1:

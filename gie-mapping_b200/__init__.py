@@ -15,5 +15,6 @@ from .engine import (  # noqa: F401
     ARR_RAY_COUNT, ARR_INST_TYPE, ARR_GLB_TYPE, ARR_EDT, ARR_AUX, ARR_COC_AUX, ARR_PAIR,
 )
 from . import scenes  # noqa: F401
+from . import replay_io  # noqa: F401
 
 __all__ = ["GieError", "LocMap", "GlbHashMap", "Mapper", "load_library", "library_path", "scenes", "STAGE_NAMES"]

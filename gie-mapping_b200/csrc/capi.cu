@@ -301,7 +301,10 @@ int gie_hashmap_create(gie_hashmap **out, gie_locmap *lm, int bucket_max, int bl
                           (m.Z + 7) / 8 + 1 + 2 * hm->halo_blocks);
     hm->tab_entries = (size_t)h.tab_dim.x * h.tab_dim.y * h.tab_dim.z;
     GIE_CUDA_CHECK(cudaMalloc(&h.btab, hm->tab_entries * 4));
-    GIE_CUDA_CHECK(cudaMalloc(&h.touched, hm->tab_entries));
+    GIE_CUDA_CHECK(cudaMalloc(&h.dirty, (size_t)block_max));
+    GIE_CUDA_CHECK(cudaMemsetAsync(h.dirty, 0, (size_t)block_max, s));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->changed_list, (size_t)block_max * sizeof(int)));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->changed_count, sizeof(int)));
     GIE_CUDA_CHECK(cudaMallocHost(&hm->status_host, sizeof(int)));
     GIE_CUDA_CHECK(cudaMallocHost(&hm->stats_host, 8 * sizeof(long long)));
     *hm->status_host = 0;
@@ -321,10 +324,10 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     HashDev &h = hm->d;
     cudaFree(h.keys); cudaFree(h.vals); cudaFree(h.block_count); cudaFree(h.status); cudaFree(h.block_keys);
     cudaFree(h.occ_val); cudaFree(h.vox_type); cudaFree(h.update_ct); cudaFree(h.coc_glb); cudaFree(h.dist_sq);
-    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched);
+    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
     cudaFree(hm->cseed_key); cudaFree(hm->counters); cudaFree(hm->barrier); cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
-    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id);
+    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace);
     cudaFreeHost(hm->status_host); cudaFreeHost(hm->stats_host);
     if (hm->lm->hm == hm) hm->lm->hm = nullptr;
     delete hm;
@@ -405,20 +408,44 @@ int gie_ogm_depth_host(gie_locmap *lm, gie_hashmap *hm, const float *img, int ro
 }
 
 // ---- per-frame stages -----------------------------------------------------------------------------------------------
-int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct)
+int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream_glb_ogm, int n_obs, const float *obs_ll,
+                           const float *obs_ur, const unsigned char *obs_activated)
 {
-    if (!hm) return GIE_ERR_INVALID_ARG;
-    return gie_launch_update_ogm(hm, input_pntcld, map_ct);
+    if (!hm || n_obs < 0 || (n_obs > 0 && (!obs_ll || !obs_ur || !obs_activated))) return GIE_ERR_INVALID_ARG;
+    // only activated boxes travel (Ext_Obs_Wrapper::bbx_H2D uploads all of them every frame, pre_map.cu:50-60);
+    // slot 0 keeps its meaning as the fence even when it is off
+    int n_dev = 0;
+    bool any = false;
+    for (int i = 0; i < n_obs; i++) any |= obs_activated[i] != 0;
+    if (any) {
+        std::vector<float> pack;
+        for (int i = 0; i < n_obs; i++) {
+            if (i > 0 && !obs_activated[i]) continue;
+            const float row[7] = { obs_ll[3 * i], obs_ll[3 * i + 1], obs_ll[3 * i + 2], obs_ur[3 * i], obs_ur[3 * i + 1], obs_ur[3 * i + 2],
+                                   obs_activated[i] ? 1.f : 0.f };
+            pack.insert(pack.end(), row, row + 7);
+        }
+        n_dev = (int)pack.size() / 7;
+        if (n_dev > hm->obs_cap) {
+            GIE_CUDA_CHECK(cudaStreamSynchronize(hm->lm->stream));
+            cudaFree(hm->obs_dev);
+            GIE_CUDA_CHECK(cudaMalloc(&hm->obs_dev, (size_t)n_dev * 2 * 7 * sizeof(float)));
+            hm->obs_cap = n_dev * 2;
+        }
+        // pageable source: the copy is staged before the call returns
+        GIE_CUDA_CHECK(cudaMemcpyAsync(hm->obs_dev, pack.data(), pack.size() * sizeof(float), cudaMemcpyHostToDevice, hm->lm->stream));
+    }
+    return gie_launch_update_ogm(hm, input_pntcld, map_ct, stream_glb_ogm, n_dev);
 }
 int gie_edt_batch_update(gie_locmap *lm)
 {
     if (!lm) return GIE_ERR_INVALID_ARG;
     return gie_launch_batch_edt(lm);
 }
-int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct)
+int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt)
 {
     if (!hm) return GIE_ERR_INVALID_ARG;
-    return gie_launch_merge(hm, map_ct);
+    return gie_launch_merge(hm, map_ct, display_glb_edt);
 }
 
 int gie_sync(gie_hashmap *hm)
@@ -467,6 +494,56 @@ int gie_hashmap_export_blocks(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel 
         GIE_CUDA_CHECK(cudaStreamSynchronize(s));
     }
     cudaFree(tmp);
+    return GIE_OK;
+}
+
+int gie_hashmap_num_changed(gie_hashmap *hm, int *n)
+{
+    if (!hm || !n) return GIE_ERR_INVALID_ARG;
+    int nb = 0, rc;
+    if ((rc = gie_hashmap_num_blocks(hm, &nb)) != GIE_OK) return rc;
+    if ((rc = gie_launch_list_changed(hm, nb, 0)) != GIE_OK) return rc;
+    GIE_CUDA_CHECK(cudaMemcpyAsync(n, hm->changed_count, sizeof(int), cudaMemcpyDeviceToHost, hm->lm->stream));
+    GIE_CUDA_CHECK(cudaStreamSynchronize(hm->lm->stream));
+    return GIE_OK;
+}
+
+int gie_hashmap_stream_changed(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel *voxels_host, int max_blocks, int *n_out)
+{
+    if (!hm || !keys_host || !voxels_host || !n_out || max_blocks < 0) return GIE_ERR_INVALID_ARG;
+    gie_locmap *lm = hm->lm;
+    cudaStream_t s = lm->stream;
+    int nb = 0, rc, n = 0;
+    if ((rc = gie_hashmap_num_blocks(hm, &nb)) != GIE_OK) return rc;
+    if ((rc = gie_launch_list_changed(hm, nb, 1)) != GIE_OK) return rc;
+    GIE_CUDA_CHECK(cudaMemcpyAsync(&n, hm->changed_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    GIE_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (n > max_blocks) {   // the caller's buffers are too small: keep the flags of the blocks that do not fit
+        // (list order is not sorted; re-flag the tail)
+        std::vector<int> tail((size_t)(n - max_blocks));
+        GIE_CUDA_CHECK(cudaMemcpy(tail.data(), hm->changed_list + max_blocks, tail.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int b : tail) GIE_CUDA_CHECK(cudaMemset(hm->d.dirty + b, 1, 1));
+        n = max_blocks;
+    }
+    *n_out = n;
+    if (n == 0) return GIE_OK;
+    // staging: keys (12 B) + voxels (20 KB) per block, gathered by one kernel and copied with one D2H each
+    const size_t vbytes = (size_t)n * 512 * sizeof(gie_glbvoxel), kbytes = (size_t)n * 3 * sizeof(int32_t);
+    if ((rc = ensure_stage(lm, vbytes + kbytes)) != GIE_OK) return rc;
+    gie_glbvoxel *vdev = (gie_glbvoxel *)lm->stage_dev;
+    int32_t *kdev = (int32_t *)((char *)lm->stage_dev + vbytes);
+    if ((rc = gie_launch_gather_changed(hm, 0, n, kdev, vdev)) != GIE_OK) return rc;
+    GIE_CUDA_CHECK(cudaMemcpyAsync(voxels_host, vdev, vbytes, cudaMemcpyDeviceToHost, s));
+    GIE_CUDA_CHECK(cudaMemcpyAsync(keys_host, kdev, kbytes, cudaMemcpyDeviceToHost, s));
+    GIE_CUDA_CHECK(cudaStreamSynchronize(s));
+    return GIE_OK;
+}
+
+int gie_debug_wave_trace(gie_hashmap *hm, unsigned long long *out, int max_levels)
+{
+    if (!hm || !out || !hm->wave_trace) { gie_set_error("wave trace is off (set GIE_WAVE_TRACE=1 before creating the map)"); return GIE_ERR_INVALID_ARG; }
+    GIE_CUDA_CHECK(cudaStreamSynchronize(hm->lm->stream));
+    GIE_CUDA_CHECK(cudaMemcpy(out, hm->wave_trace, (size_t)4096 * 10 * 8, cudaMemcpyDeviceToHost));
     return GIE_OK;
 }
 

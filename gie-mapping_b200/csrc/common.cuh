@@ -65,7 +65,7 @@ struct HashDev {
     unsigned long long *pair;
     // per-frame dense block table around the local volume (one hash probe per block, not per voxel)
     int32_t *btab;
-    uint8_t *touched;
+    uint8_t *dirty;            // per block: changed since the last gie_hashmap_stream_changed (reference: stream_VB_keys_D)
     int3 tab_org;   // block coords of table entry (0,0,0)
     int3 tab_dim;
 };

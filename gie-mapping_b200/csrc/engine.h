@@ -40,7 +40,7 @@ struct gie_hashmap {
     // wavefront queues
     unsigned long long *qA[3]{};  // outside queues: packed global coords
     unsigned long long *qB[3]{};
-    int32_t *qC[3]{};             // inside queue: linear local index
+    unsigned long long *qC[3]{};  // inside queue: (pusher coc id << 32) | packed local coords
     unsigned long long *cseed_key = nullptr;  // deferred C-seed pair updates (same slots as qC[0])
     int queue_cap = 0;
     int *counters = nullptr;      // device ints, see wave.cu
@@ -52,6 +52,14 @@ struct gie_hashmap {
     int32_t *decA_flags = nullptr;
     uint32_t *snap_id = nullptr;  // per-queue-slot snapshot for waves B/C
     int wave_ctas = 0;
+    int wave_cluster = 1;         // CTAs per thread-block cluster of the wave kernel
+    unsigned long long *wave_trace = nullptr;   // diagnostics, allocated when GIE_WAVE_TRACE is set
+    // external-obstacle boxes of the current frame: [n][7] = ll.xyz, ur.xyz, activated
+    float *obs_dev = nullptr;
+    int obs_cap = 0;
+    // streaming scratch: compacted list of changed blocks
+    int *changed_list = nullptr;
+    int *changed_count = nullptr;
     int *status_host = nullptr;   // pinned
     long long *stats_host = nullptr;  // pinned [8]
 };
@@ -81,11 +89,13 @@ int gie_launch_ogm_depth(gie_locmap *lm, gie_hashmap *hm, const float *img, int 
                          float fx, float fy, int valid_nan, int fmp, int r2);
 // hashmap.cu
 int gie_hash_begin_frame(gie_hashmap *hm);                       // sets the table origin, clears touched flags
-int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct);
+int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream_glb_ogm, int n_obs);
 int gie_launch_export(gie_hashmap *hm, int nblocks, gie_glbvoxel *out_dev);
+int gie_launch_list_changed(gie_hashmap *hm, int nblocks, int clear);   // -> changed_list / changed_count
+int gie_launch_gather_changed(gie_hashmap *hm, int first, int n, int32_t *keys_dev, gie_glbvoxel *out_dev);
 // edt.cu
 int gie_edt_prepare(gie_locmap *lm);
 int gie_launch_batch_edt(gie_locmap *lm);
 // wave.cu
 int gie_wave_prepare(gie_hashmap *hm);
-int gie_launch_merge(gie_hashmap *hm, int map_ct);
+int gie_launch_merge(gie_hashmap *hm, int map_ct, int display_glb_edt);

@@ -70,8 +70,23 @@ __device__ __forceinline__ void set_occ_val(uint8_t &occ, int8_t &type, float va
 
 // updateHashOGMWithPntCld / updateHashOGMWithSensor.  Each thread owns VEC consecutive voxels along x (vector loads /
 // stores on the dense arrays); a grid-stride loop over a grid sized to the SM count keeps CTAs resident.
+// external obstacles (unify_helper.cuh:68-86,149-162; insideAABB voxmap_utils.cuh:203-207): box 0 is a fence (obstacle
+// when OUTSIDE it), boxes 1.. are obstacles inside.  obs[i] = {ll.xyz, ur.xyz, activated}
+__device__ __forceinline__ bool ext_obs_flag(const LocDev &m, int3 glb, int n_obs, const float *__restrict__ obs)
+{
+    const float px = (float)glb.x * m.w, py = (float)glb.y * m.w, pz = (float)glb.z * m.w;
+    for (int i = 0; i < n_obs; i++) {
+        const float *o = obs + 7 * i;
+        if (__ldg(&o[6]) == 0.f) continue;
+        bool in = (px >= __ldg(&o[0]) && py >= __ldg(&o[1]) && pz >= __ldg(&o[2])) && (px <= __ldg(&o[3]) && py <= __ldg(&o[4]) && pz <= __ldg(&o[5]));
+        if (i == 0) { if (!in) return true; }
+        else if (in) return true;
+    }
+    return false;
+}
+
 template <bool PNTCLD, int VEC>
-__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct)
+__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs)
 {
     const int nq = m.N / VEC;                       // X % VEC == 0, so a group never straddles a row
     const int nq_pad = (nq + 31) & ~31;             // whole warps run the collective below
@@ -102,8 +117,8 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
             const int ti = gie_tab_index(h, glb);
             int blk = __ldcg(&h.btab[ti]);
             // warp-aggregated allocation: one lane per distinct missing block inserts, the others take its result
-            {
-                const bool need = blk < 0 && observed;
+            const bool need = blk < 0 && observed;
+            if (__any_sync(0xffffffffu, need)) {   // rare after the first frames: blocks already exist
                 unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
                 int leader = __ffs(grp) - 1;
                 int res = -1;
@@ -118,20 +133,23 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
             if (valid && blk >= 0) {
                 size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
                 type = h.vox_type[vi];
-                if (observed) {
+                const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
+                if (observed || occ_flag) {
+                    const int8_t old_type = type;
                     uint8_t occ = h.occ_val[vi];
                     if (PNTCLD) {
-                        if (cnt[k] > 0) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
+                        if (cnt[k] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
                         else {
                             float p = fminf(1.f, __fdiv_rn((float)(-cnt[k]), 10.f));
                             set_occ_val(occ, type, 0.f, p, m.thresh);
                         }
                     } else {
-                        if (inst[k] == GIE_VOX_OCCUPIED) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
+                        if (inst[k] == GIE_VOX_OCCUPIED || occ_flag) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
                         else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
                     }
                     h.occ_val[vi] = occ;
                     h.vox_type[vi] = type;
+                    if (stream && type != old_type) h.dirty[blk] = 1;
                 }
             }
             out_type[k] = type;
@@ -149,6 +167,77 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
     }
 }
 
+// Allocation-only pre-pass, used when external-obstacle boxes are active: the reference allocates every touched block
+// before the merge (allocHashTB), so a box voxel must see a block that another voxel's observation creates this frame.
+template <bool PNTCLD>
+__global__ void __launch_bounds__(256) k_alloc_observed(LocDev m, HashDev h)
+{
+    const int n_pad = (m.N + 31) & ~31;
+    const int lane = threadIdx.x & 31;
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n_pad; id += gridDim.x * blockDim.x) {
+        const bool valid = id < m.N;
+        bool observed = false;
+        int ti = -1;
+        int3 glb = make_int3(0, 0, 0);
+        if (valid) {
+            observed = PNTCLD ? (m.ray_count[id] != 0) : (m.inst_type[id] == GIE_VOX_OCCUPIED || m.inst_type[id] == GIE_VOX_FREE);
+            glb = make_int3(id % m.X, (id / m.X) % m.Y, id / (m.X * m.Y)) + m.pvt;
+            ti = gie_tab_index(h, glb);
+        }
+        const bool need = observed && __ldcg(&h.btab[ti]) < 0;
+        unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
+        if (need && lane == __ffs(grp) - 1) {
+            int res = hash_insert(h, gie_vb_key(glb));
+            if (res >= 0) h.btab[ti] = res;
+        }
+    }
+}
+
+// ordered list of the blocks whose dirty flag is set (one CTA-wide scan per 1024 blocks, atomics only per CTA)
+__global__ void __launch_bounds__(256) k_list_changed(HashDev h, int nblocks, int *list, int *count, int clear)
+{
+    __shared__ int base;
+    __shared__ int wcnt[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int b0 = blockIdx.x * blockDim.x; b0 < nblocks; b0 += gridDim.x * blockDim.x) {
+        int b = b0 + threadIdx.x;
+        bool d = b < nblocks && h.dirty[b] != 0;
+        unsigned bal = __ballot_sync(0xffffffffu, d);
+        if (lane == 0) wcnt[wid] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int tot = 0;
+            for (int i = 0; i < 8; i++) { int c = wcnt[i]; wcnt[i] = tot; tot += c; }
+            base = tot ? atomicAdd(count, tot) : 0;
+        }
+        __syncthreads();
+        if (d) {
+            list[base + wcnt[wid] + __popc(bal & ((1u << lane) - 1))] = b;
+            if (clear) h.dirty[b] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+// GlbHashMap::streamPipeline's device half (glb_hash_map.cu:232-244, getUpdatedAddr unify_helper.cuh:11-32): gather the
+// listed blocks into the reference's AoS GlbVoxel layout / voxel order, one CTA per block
+__global__ void __launch_bounds__(512) k_gather_changed(HashDev h, const int *__restrict__ list, int first, int32_t *keys, gie_glbvoxel *out)
+{
+    const int b = list[first + blockIdx.x];
+    const int v = threadIdx.x;                   // engine order (z&7)*64 + (y&7)*8 + (x&7)
+    const size_t i = (size_t)b * 512 + v;
+    int3 l = make_int3(v & 7, (v >> 3) & 7, v >> 6);
+    gie_glbvoxel o;
+    o.occ_val = h.occ_val[i]; o.vox_type = h.vox_type[i]; o.update_ct = h.update_ct[i];
+    int3 coc = gie_unpack_coc(h.coc_glb[i]);
+    o.coc_glb[0] = coc.x; o.coc_glb[1] = coc.y; o.coc_glb[2] = coc.z;
+    o.dist_sq = h.dist_sq[i]; o.wave_layer = h.wave_layer[i];
+    unsigned long long p = h.pair[i];
+    o.dist_id_pair = (p >> 32) | (p << 32);      // reference word order: sq_dist[0] = dist, parent_loc_id[1] = id
+    out[(size_t)blockIdx.x * 512 + gie_ref_vox_in_block(l)] = o;
+    if (v < 3) { int3 k = h.block_keys[b]; keys[3 * blockIdx.x + v] = v == 0 ? k.x : (v == 1 ? k.y : k.z); }
+}
+
 __global__ void k_export(HashDev h, int nblocks, gie_glbvoxel *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -159,7 +248,9 @@ __global__ void k_export(HashDev h, int nblocks, gie_glbvoxel *out)
     o.occ_val = h.occ_val[i]; o.vox_type = h.vox_type[i]; o.update_ct = h.update_ct[i];
     int3 coc = gie_unpack_coc(h.coc_glb[i]);
     o.coc_glb[0] = coc.x; o.coc_glb[1] = coc.y; o.coc_glb[2] = coc.z;
-    o.dist_sq = h.dist_sq[i]; o.wave_layer = h.wave_layer[i]; o.dist_id_pair = h.pair[i];
+    o.dist_sq = h.dist_sq[i]; o.wave_layer = h.wave_layer[i];
+    unsigned long long p = h.pair[i];
+    o.dist_id_pair = (p >> 32) | (p << 32);      // reference word order: sq_dist[0] = dist, parent_loc_id[1] = id
     out[(size_t)b * 512 + gie_ref_vox_in_block(l)] = o;
 }
 
@@ -176,21 +267,50 @@ int gie_hash_begin_frame(gie_hashmap *hm)
     return GIE_OK;
 }
 
-int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct)
+int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream, int n_obs)
 {
+    const float *obs = hm->obs_dev;
     gie_locmap *lm = hm->lm;
     StageTimer t(lm, GIE_ST_HASH_MERGE);
     const int vec = (lm->d.X % 4 == 0) ? 4 : 1;
     long long groups = (long long)lm->d.N / vec;
     int grid = (int)std::min<long long>((groups + 255) / 256, (long long)lm->num_sms * 16);
+    if (n_obs > 0) {
+        int g1 = (int)std::min<long long>(((long long)lm->d.N + 255) / 256, (long long)lm->num_sms * 16);
+        if (input_pntcld) k_alloc_observed<true><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
+        else k_alloc_observed<false><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
+        lm->launches++;
+    }
     if (vec == 4) {
-        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
-        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
+        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
     } else {
-        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
-        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct);
+        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
+        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
     }
     lm->launches++;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
+int gie_launch_list_changed(gie_hashmap *hm, int nblocks, int clear)
+{
+    gie_locmap *lm = hm->lm;
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->changed_count, 0, sizeof(int), lm->stream));
+    if (nblocks > 0) {
+        int grid = std::min((nblocks + 255) / 256, lm->num_sms * 8);
+        k_list_changed<<<grid, 256, 0, lm->stream>>>(hm->d, nblocks, hm->changed_list, hm->changed_count, clear);
+        lm->launches++;
+    }
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
+int gie_launch_gather_changed(gie_hashmap *hm, int first, int n, int32_t *keys_dev, gie_glbvoxel *out_dev)
+{
+    if (n <= 0) return GIE_OK;
+    k_gather_changed<<<n, 512, 0, hm->lm->stream>>>(hm->d, hm->changed_list, first, keys_dev, out_dev);
+    hm->lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

@@ -19,14 +19,43 @@
 
 namespace {
 
+constexpr int WAVE_THREADS = 512;   // one CTA per SM: the grid barrier costs grow with the number of CTAs
+
 // counters layout (ints)
 enum { C_A0 = 0, C_B0 = 3, C_C0 = 6, C_LEVA = 10, C_LEVB = 11, C_LEVC = 12, C_FA = 13, C_FB = 14, C_FC = 15,
-       C_FB_AFTER_A = 16, C_FC_AFTER_B = 17, C_COUNT = 32 };
+       C_FB_AFTER_A = 16, C_FC_AFTER_B = 17, C_CUR_LEVEL = 18, C_COUNT = 32 };
+
+// cluster-local mode of wave C (see wave_c_local): per-CTA frontier queues in shared memory
+constexpr int LQ_CAP = 2048;
+struct LocalQ {
+    unsigned long long q[2][LQ_CAP];
+    uint32_t snap[LQ_CAP];
+    int n[2];
+    int total, nmax;
+    int spill_base;
+};
+
+// Wave-C queue entry.  low word: local voxel coords packed 10/10/10 (X, Y <= 1024, Z <= 1022), so that no kernel has to
+// divide a linear index back into coordinates; high word: the coc id the PUSHER offered.  De-duplication is by that id:
+// a voxel lowered by several neighbours in one level is queued once per successful atomicMin, and only the copy whose id
+// equals the voxel's final pair id is processed (exactly one: a later offer only gets in if it is strictly smaller).  The
+// reference (and the oracle) de-duplicate with a gray/black colour per voxel instead (wave_core.cuh:372-389); the set of
+// voxels processed per level is the same, without the extra atomicExch round trip per relaxation.
+#define C_ALWAYS 0xffffffffu   // seeds: already unique (colour 1 in k_frontiers / wave B), always processed
+__device__ __forceinline__ unsigned long long c_entry(int3 c, uint32_t sid)
+{
+    return ((unsigned long long)sid << 32) | (uint32_t)(c.x | (c.y << 10) | (c.z << 20));
+}
+__device__ __forceinline__ int3 c_entry_coord(unsigned long long e)
+{
+    uint32_t p = (uint32_t)e;
+    return make_int3((int)(p & 1023), (int)((p >> 10) & 1023), (int)(p >> 20));
+}
 
 struct WaveDev {
     unsigned long long *qA[3];
     unsigned long long *qB[3];
-    int32_t *qC[3];
+    unsigned long long *qC[3];   // inside queue: (pusher coc id << 32) | packed local coords, see c_entry
     unsigned long long *cseed_key;
     int cap;
     int *cnt;
@@ -36,7 +65,18 @@ struct WaveDev {
     unsigned long long *dec_pair;
     int32_t *dec_flags;
     uint32_t *snap_id;
+    int display;   // display_glb_edt: record changed blocks for streaming
+    int cluster_size, local_enter, local_spill;   // cluster-local mode of wave C
+
+    unsigned long long *trace;   // diagnostics (GIE_WAVE_TRACE=1): per wave-C level {n, t0, t_phase1, t_bar1, t_phase2, t_bar2} in ns
 };
+constexpr int TRACE_LEVELS = 4096;
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
 
 __constant__ int3 DIRS6[6] = { { -1, 0, 0 }, { 1, 0, 0 }, { 0, -1, 0 }, { 0, 1, 0 }, { 0, 0, -1 }, { 0, 0, 1 } };
 
@@ -193,7 +233,7 @@ __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev 
                     if (lowered) {                                   // lower-in seed (frontier C)
                         wl = 1;
                         int i = atomicAdd(&w.cnt[C_C0], 1);
-                        if (i < w.cap) { w.qC[0][i] = id; w.cseed_key[i] = new_key; }
+                        if (i < w.cap) { w.qC[0][i] = c_entry(c, C_ALWAYS); w.cseed_key[i] = new_key; }
                         else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
                     }
                     if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
@@ -208,18 +248,61 @@ __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Grid barrier for the persistent wave kernel.  A flat atomic counter costs ~27 cycles of L2 atomic-unit time per arriving
+// CTA (same-address atomics serialise), i.e. microseconds per barrier; here every CTA publishes its arrival with a plain
+// release store to its OWN 128-byte line, CTA 0 polls all lines in parallel (one thread per line) and releases the grid with
+// one store that the other CTAs poll.  bar[32 * cta] = arrival generation of that CTA, bar[32 * gridDim.x] = release.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &gen)
 {
+    gen++;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        gen++;
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned int target = gen * gridDim.x;
-        while (*((volatile unsigned int *)bar) < target) { __nanosleep(20); }
-        __threadfence();
+    unsigned *release = bar + 32 * gridDim.x;
+    if (blockIdx.x == 0) {
+        for (int c = 1 + threadIdx.x; c < gridDim.x; c += blockDim.x)
+            while (ld_acquire_gpu(bar + 32 * c) < gen) { }
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); st_release_gpu(release, gen); }
+    } else {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_release_gpu(bar + 32 * blockIdx.x, gen);
+            while (ld_acquire_gpu(release) < gen) { }
+            __threadfence();
+        }
+        __syncthreads();
     }
-    __syncthreads();
+}
+
+// Queue push aggregated per warp: every lane of a converged warp calls it with its own items (0..6); one atomicAdd per warp.
+template <typename T>
+__device__ __forceinline__ void q_push_warp(T *q, int *cnt, int cap, const T *items, int n_items, int *status)
+{
+    const int lane = threadIdx.x & 31;
+    int incl = n_items;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0) return;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(cnt, total);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - n_items;
+    for (int k = 0; k < n_items; k++) {
+        if (base + k >= cap) { atomicOr(status, GIE_DEV_ERR_QUEUE_OVERFLOW); break; }
+        q[base + k] = items[k];
+    }
 }
 
 // wave A: raise_outside (wave_core.cuh:103-224), phase 1 = offers + own decision, phase 2 = apply
@@ -233,6 +316,7 @@ __device__ void waveA_phase1(const LocDev &m, const HashDev &h, const WaveDev &w
         if (!vox_ref(h, cg, vi)) continue;
         int o_dist = __ldcg(&h.dist_sq[vi]);
         if (o_dist > m.cutoff_sq) continue;
+        if (w.display) h.dirty[vi >> 9] = 1;   // wave_core.cuh:128-134
         int3 lcoc = gie_unpack_coc(__ldcg(&h.coc_glb[vi]));
         int3 o_coc = lcoc;
         unsigned long long o_pair = __ldcg(&h.pair[vi]);
@@ -307,6 +391,7 @@ __device__ void waveB_phase1(const LocDev &m, const HashDev &h, const WaveDev &w
         w.snap_id[i] = 0xffffffffu;
         if (!vox_ref(h, unpack_glb(__ldcg(&cur[i])), vi)) continue;
         h.wave_layer[vi] = GIE_WL_BLACK;
+        if (w.display) h.dirty[vi >> 9] = 1;   // wave_core.cuh:250-256
         if (__ldcg(&h.dist_sq[vi]) > m.cutoff_sq) continue;
         unsigned long long p = __ldcg(&h.pair[vi]);
         uint32_t id = gie_pair_id(p);
@@ -318,74 +403,230 @@ __device__ void waveB_phase1(const LocDev &m, const HashDev &h, const WaveDev &w
 __device__ void waveB_phase2(const LocDev &m, const HashDev &h, const WaveDev &w, int map_ct, const unsigned long long *cur,
                              int n, unsigned long long *next, int *next_cnt, int gray, int tid, int nthreads)
 {
-    for (int i = tid; i < n; i += nthreads) {
-        uint32_t sid = w.snap_id[i];
-        if (sid == 0xffffffffu) continue;
-        int3 cg = unpack_glb(__ldcg(&cur[i]));
-        int3 coc = gie_id2wr(sid) + m.upvt;
-        for (int d = 0; d < 6; d++) {
-            int3 ng = cg + DIRS6[d];
-            int3 nb = ng - m.pvt;
-            int cand = sqd3(coc, ng);
-            unsigned long long key = gie_mk_pair(cand, sid);
-            if (!gie_inside_loc(m, nb)) {
-                size_t ni;
-                if (!vox_ref(h, ng, ni)) continue;
-                if (h.vox_type[ni] == GIE_VOX_UNKNOWN) continue;
-                if (gie_invalid_coc_glb(gie_unpack_coc(__ldcg(&h.coc_glb[ni])))) continue;
-                unsigned long long old = atomicMin(&h.pair[ni], key);
-                if (key < old) {
-                    int color = atomicExch(&h.wave_layer[ni], gray);
-                    if (color == gray) continue;
-                    h.update_ct[ni] = map_ct;
-                    q_push(next, next_cnt, w.cap, pack_glb(ng), h.status);
-                }
-            } else {
-                int nid = gie_lidx(m, nb);
-                if (m.aux[nid] > cand) {
-                    atomicMin(&m.pair[nid], key);
-                    if (atomicExch(&m.wave_layer[nid], 1) != 1)
-                        q_push(w.qC[0], &w.cnt[C_C0], w.cap, (int32_t)nid, h.status);
+    const int lane = threadIdx.x & 31;
+    for (int i0 = tid - lane; i0 < n; i0 += nthreads) {   // warp-uniform trip count: the pushes below are warp collectives
+        const int i = i0 + lane;
+        unsigned long long out_items[6];
+        unsigned long long in_items[6];
+        int n_out = 0, n_in = 0;
+        uint32_t sid = i < n ? w.snap_id[i] : 0xffffffffu;
+        if (sid != 0xffffffffu) {
+            int3 cg = unpack_glb(__ldcg(&cur[i]));
+            int3 coc = gie_id2wr(sid) + m.upvt;
+            // the six relaxations are independent: issue every atomicMin before looking at any result
+            unsigned long long key[6], old[6];
+            size_t ni[6];
+            int nid[6], kind[6];   // 0 = skip, 1 = outside (hash voxel), 2 = inside (local volume)
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                int3 ng = cg + DIRS6[d];
+                int3 nb = ng - m.pvt;
+                int cand = sqd3(coc, ng);
+                key[d] = gie_mk_pair(cand, sid);
+                kind[d] = 0; old[d] = 0; ni[d] = 0; nid[d] = 0;
+                if (!gie_inside_loc(m, nb)) {
+                    if (!vox_ref(h, ng, ni[d])) continue;
+                    if (h.vox_type[ni[d]] == GIE_VOX_UNKNOWN) continue;
+                    if (gie_invalid_coc_glb(gie_unpack_coc(__ldcg(&h.coc_glb[ni[d]])))) continue;
+                    kind[d] = 1;
+                    old[d] = atomicMin(&h.pair[ni[d]], key[d]);
+                } else {
+                    nid[d] = gie_lidx(m, nb);
+                    if (m.aux[nid[d]] > cand) { kind[d] = 2; atomicMin(&m.pair[nid[d]], key[d]); }
                 }
             }
+            int col[6];
+#pragma unroll
+            for (int d = 0; d < 6; d++) {   // colour swaps all in flight before any is looked at
+                col[d] = kind[d] == 1 ? gray : 1;
+                if (kind[d] == 1 && key[d] < old[d]) col[d] = atomicExch(&h.wave_layer[ni[d]], gray);
+                else if (kind[d] == 2) col[d] = atomicExch(&m.wave_layer[nid[d]], 1);
+            }
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                if (kind[d] == 1 && col[d] != gray) {
+                    h.update_ct[ni[d]] = map_ct;
+                    out_items[n_out++] = pack_glb(cg + DIRS6[d]);
+                } else if (kind[d] == 2 && col[d] != 1) in_items[n_in++] = c_entry(cg + DIRS6[d] - m.pvt, C_ALWAYS);
+            }
         }
+        q_push_warp(next, next_cnt, w.cap, out_items, n_out, h.status);
+        q_push_warp(w.qC[0], &w.cnt[C_C0], w.cap, in_items, n_in, h.status);
     }
 }
 
 // wave C: lower_inside (wave_core.cuh:353-393)
-__device__ void waveC_phase1(const LocDev &m, const WaveDev &w, const int32_t *cur, int n, int tid, int nthreads)
+// the six relaxations of one frontier voxel: keys from the voxel's snapshot coc, all atomicMins in flight together
+struct CRelax { unsigned long long key[6], old[6]; int3 nb[6]; bool in[6]; };
+__device__ __forceinline__ void c_relax(const LocDev &m, int3 c, uint32_t sid, CRelax &r)
 {
-    for (int i = tid; i < n; i += nthreads) {
-        int id = __ldcg(&cur[i]);
-        m.wave_layer[id] = GIE_WL_BLACK;
-        w.snap_id[i] = gie_pair_id(__ldcg(&m.pair[id]));
+    const int id = gie_lidx(m, c);
+    const int XY = m.X * m.Y;
+    const int3 dlt = gie_id2wr(sid) + m.upvt - m.pvt - c;           // coc - voxel
+    const int d0 = dlt.x * dlt.x + dlt.y * dlt.y + dlt.z * dlt.z;
+    // |coc - (c + e)|^2 = d0 - 2 e.dlt + 1 for a unit step e
+    const int dd[6] = { d0 + 2 * dlt.x + 1, d0 - 2 * dlt.x + 1, d0 + 2 * dlt.y + 1, d0 - 2 * dlt.y + 1, d0 + 2 * dlt.z + 1, d0 - 2 * dlt.z + 1 };
+    const int off[6] = { -1, 1, -m.X, m.X, -XY, XY };
+    const bool ok[6] = { c.x > 0, c.x < m.X - 1, c.y > 0, c.y < m.Y - 1, c.z > 0, c.z < m.Z - 1 };
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+        r.in[d] = ok[d];
+        r.nb[d] = c + DIRS6[d];
+        r.key[d] = gie_mk_pair(dd[d], sid);
+        r.old[d] = ok[d] ? atomicMin(&m.pair[id + off[d]], r.key[d]) : 0ULL;
     }
 }
-__device__ void waveC_phase2(const LocDev &m, const HashDev &h, const WaveDev &w, const int32_t *cur, int n, int32_t *next,
-                             int *next_cnt, int gray, int tid, int nthreads)
+__device__ void waveC_phase1(const LocDev &m, const WaveDev &w, const unsigned long long *cur, int n, int tid, int nthreads)
 {
-    const int XY = m.X * m.Y;
     for (int i = tid; i < n; i += nthreads) {
-        int id = __ldcg(&cur[i]);
-        uint32_t sid = w.snap_id[i];
-        int3 cb = make_int3(id % m.X, (id / m.X) % m.Y, id / XY);
-        int3 coc_buf = gie_id2wr(sid) + m.upvt - m.pvt;
-        for (int d = 0; d < 6; d++) {
-            int3 nb = cb + DIRS6[d];
-            if (!gie_inside_loc(m, nb)) continue;
-            int nid = gie_lidx(m, nb);
-            unsigned long long key = gie_mk_pair(sqd3(coc_buf, nb), sid);
-            unsigned long long old = atomicMin(&m.pair[nid], key);
-            if (key < old) {
-                if (atomicExch(&m.wave_layer[nid], gray) == gray) continue;
-                q_push(next, next_cnt, w.cap, (int32_t)nid, h.status);
-            }
+        unsigned long long e = __ldcg(&cur[i]);
+        uint32_t want = (uint32_t)(e >> 32);
+        uint32_t sid = gie_pair_id(__ldcg(&m.pair[gie_lidx(m, c_entry_coord(e))]));
+        w.snap_id[i] = (want == C_ALWAYS || want == sid) ? sid : 0xffffffffu;   // 0xffffffff: a superseded copy, skipped
+    }
+}
+__device__ void waveC_phase2(const LocDev &m, const HashDev &h, const WaveDev &w, const unsigned long long *cur, int n,
+                             unsigned long long *next, int *next_cnt, int tid, int nthreads)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i0 = tid - lane; i0 < n; i0 += nthreads) {   // warp-uniform trip count (warp-collective push)
+        const int i = i0 + lane;
+        unsigned long long items[6];
+        int n_items = 0;
+        uint32_t sid = i < n ? w.snap_id[i] : 0xffffffffu;
+        if (sid != 0xffffffffu) {
+            CRelax r;
+            c_relax(m, c_entry_coord(__ldcg(&cur[i])), sid, r);
+#pragma unroll
+            for (int d = 0; d < 6; d++)
+                if (r.in[d] && r.key[d] < r.old[d]) items[n_items++] = c_entry(r.nb[d], sid);
         }
+        q_push_warp(next, next_cnt, w.cap, items, n_items, h.status);
     }
 }
 
-__global__ void __launch_bounds__(256) k_waves(LocDev m, HashDev h, WaveDev w, int map_ct)
+// Wave C while the frontier is small (the common case: a few hundred to a few thousand voxels per level for hundreds of
+// levels).  A grid-wide level costs two grid barriers plus global-queue round trips (~11 us measured); here ONE thread-block
+// cluster runs the levels on its own: every CTA keeps its share of the frontier in shared memory, pushes go to a peer CTA's
+// queue through distributed shared memory (one remote atomicAdd per warp + remote stores), and the two per-level
+// synchronisations are hardware cluster barriers.  The relaxation itself is c_relax, as in the grid-wide phases, so results
+// do not depend on the mode.  Returns the level reached; on return either the frontier is empty (all three queue counters
+// are 0) or it was spilled to the global queue of that level (too large for the cluster).
+__device__ int wave_c_local(const LocDev &m, const HashDev &h, const WaveDev &w, LocalQ &lq, int level, int n_in, int spill_at)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int R = (int)cl.num_blocks(), r = (int)cl.block_rank();
+    const int t = threadIdx.x, T = blockDim.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) { lq.n[0] = r < n_in ? (n_in - r + R - 1) / R : 0; lq.n[1] = 0; }
+    {
+        const unsigned long long *src = w.qC[level % 3];
+        for (int i = r + t * R; i < n_in; i += T * R) lq.q[0][i / R] = __ldcg(&src[i]);
+    }
+    cl.sync();   // every CTA of the cluster has taken its share: the global counters can be cleared
+    if (r == 0 && t == 0) { w.cnt[C_C0] = 0; w.cnt[C_C0 + 1] = 0; w.cnt[C_C0 + 2] = 0; }
+    int cb = 0;
+    for (;;) {
+        const int nloc = min(lq.n[cb], LQ_CAP);
+        unsigned long long *ovf_q = w.qC[(level + 1) % 3];
+        int *ovf_cnt = &w.cnt[C_C0 + (level + 1) % 3];
+        const bool tr = w.trace && r == 0 && t == 0 && level < TRACE_LEVELS;
+        if (tr) { w.trace[level * 6] = 1000000000ULL + nloc; w.trace[level * 6 + 1] = gtimer(); }
+        // phase 1: snapshot (waveC_phase1)
+        for (int k = t; k < nloc; k += T) {
+            unsigned long long e = lq.q[cb][k];
+            uint32_t want = (uint32_t)(e >> 32);
+            uint32_t sid = gie_pair_id(__ldcg(&m.pair[gie_lidx(m, c_entry_coord(e))]));
+            lq.snap[k] = (want == C_ALWAYS || want == sid) ? sid : 0xffffffffu;
+        }
+        if (t == 0) lq.n[cb ^ 1] = 0;
+        if (tr) w.trace[level * 6 + 2] = gtimer();
+        cl.sync();   // all snapshots taken, all next-queue counters zero
+        if (tr) w.trace[level * 6 + 3] = gtimer();
+        // phase 2: offers (waveC_phase2).  The lowered neighbours of one warp's 32 frontier voxels go, as one block, to the
+        // queue of a peer CTA chosen round-robin per warp and level: one remote atomicAdd per warp instead of one per voxel
+        // (same-address atomics on a queue counter serialise at a few ns each).
+        for (int k0 = t - lane; k0 < nloc; k0 += T) {   // warp-uniform trip count (warp collectives below)
+            const int k = k0 + lane;
+            uint32_t sid = k < nloc ? lq.snap[k] : 0xffffffffu;
+            CRelax rx;
+#pragma unroll
+            for (int d = 0; d < 6; d++) { rx.in[d] = false; rx.key[d] = 0; rx.old[d] = 0; rx.nb[d] = make_int3(0, 0, 0); }
+            if (sid != 0xffffffffu) c_relax(m, c_entry_coord(lq.q[cb][k]), sid, rx);
+            if (tr) {
+#pragma unroll
+                for (int d = 0; d < 6; d++) asm volatile("" ::"l"(rx.old[d]));
+                w.trace[TRACE_LEVELS * 6 + level * 4 + 0] = gtimer();
+            }
+            int mine = 0;
+#pragma unroll
+            for (int d = 0; d < 6; d++) {
+                rx.in[d] = rx.in[d] && rx.key[d] < rx.old[d];   // lowered -> joins the next frontier
+                mine += rx.in[d];
+            }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                const int dst = (wid + r + level) % R;
+                int base = 0;
+                if (lane == 31) base = atomicAdd(cl.map_shared_rank(&lq.n[cb ^ 1], dst), total);
+                base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+                if (tr) { asm volatile("" ::"r"(base)); w.trace[TRACE_LEVELS * 6 + level * 4 + 1] = gtimer(); }
+                unsigned long long *dq = cl.map_shared_rank(&lq.q[cb ^ 1][0], dst);
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    if (!rx.in[d]) continue;
+                    unsigned long long e = c_entry(rx.nb[d], sid);
+                    if (base < LQ_CAP) dq[base] = e;
+                    else {   // that CTA's queue is full: the voxel goes to the global queue of the next level
+                        int g = atomicAdd(ovf_cnt, 1);
+                        if (g < w.cap) ovf_q[g] = e; else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
+                    }
+                    base++;
+                }
+            }
+        }
+        if (tr) w.trace[level * 6 + 4] = gtimer();
+        cl.sync();   // all pushes have landed
+        if (tr) w.trace[TRACE_LEVELS * 6 + level * 4 + 2] = gtimer();
+        level++; cb ^= 1;
+        if (t < 32) {   // frontier size of the new level: every CTA reads all queue counters and reaches the same decision
+            int c = t < R ? *cl.map_shared_rank(&lq.n[cb], t) : 0;
+            int sum = c, mx = c;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+            if (t == 0) { lq.total = sum; lq.nmax = mx; }
+        }
+        __syncthreads();
+        if (tr) w.trace[(level - 1) * 6 + 5] = gtimer();
+        const int total = lq.total;
+        if (total == 0) break;
+        if (lq.nmax > LQ_CAP || total > spill_at) {
+            // hand the frontier to the grid-wide mode: append the local queues to the global queue of this level
+            const int mine = min(lq.n[cb], LQ_CAP);
+            if (t == 0) lq.spill_base = atomicAdd(&w.cnt[C_C0 + level % 3], mine);
+            __syncthreads();
+            unsigned long long *dst = w.qC[level % 3];
+            for (int k = t; k < mine; k += T) {
+                int g = lq.spill_base + k;
+                if (g < w.cap) dst[g] = lq.q[cb][k]; else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
+            }
+            break;
+        }
+    }
+    if (r == 0 && t == 0) w.cnt[C_CUR_LEVEL] = level;
+    cl.sync();   // no CTA leaves while a peer may still read its shared memory
+    return level;
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS, 1) k_waves(LocDev m, HashDev h, WaveDev w, int map_ct)
+{
+    __shared__ LocalQ lq;
     unsigned int gen = 0;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nthreads = gridDim.x * blockDim.x;
@@ -393,7 +634,7 @@ __global__ void __launch_bounds__(256) k_waves(LocDev m, HashDev h, WaveDev w, i
     // phase 0: apply the deferred frontier-C seeds
     {
         int n = min(cnt[C_C0], w.cap);
-        for (int i = tid; i < n; i += nthreads) m.pair[__ldcg(&w.qC[0][i])] = __ldcg(&w.cseed_key[i]);
+        for (int i = tid; i < n; i += nthreads) m.pair[gie_lidx(m, c_entry_coord(__ldcg(&w.qC[0][i])))] = __ldcg(&w.cseed_key[i]);
         if (tid == 0) { w.cnt[C_FA] = min(cnt[C_A0], w.cap); w.cnt[C_FB] = min(cnt[C_B0], w.cap); w.cnt[C_FC] = n; }
     }
     grid_barrier(w.barrier, gen);
@@ -429,12 +670,24 @@ __global__ void __launch_bounds__(256) k_waves(LocDev m, HashDev h, WaveDev w, i
             int ci = level % 3, ni = (level + 1) % 3, zi = (level + 2) % 3;
             int n = min(cnt[C_C0 + ci], w.cap);
             if (n == 0) break;
+            if (n <= w.local_enter) {
+                grid_barrier(w.barrier, gen);   // every CTA has read n: the counters may change now
+                if (blockIdx.x < w.cluster_size) wave_c_local(m, h, w, lq, level, n, w.local_spill);
+                grid_barrier(w.barrier, gen);
+                level = cnt[C_CUR_LEVEL] - 1;   // the loop increment brings it to the level the local mode stopped at
+                continue;
+            }
             if (tid == 0) w.cnt[C_C0 + zi] = 0;
-            int gray = (level & 1) ? GIE_WL_GRAY1 : GIE_WL_GRAY0;
+            const bool tr = w.trace && tid == 0 && level < TRACE_LEVELS;
+            if (tr) { w.trace[level * 6] = n; w.trace[level * 6 + 1] = gtimer(); }
             waveC_phase1(m, w, w.qC[ci], n, tid, nthreads);
+            if (tr) w.trace[level * 6 + 2] = gtimer();
             grid_barrier(w.barrier, gen);
-            waveC_phase2(m, h, w, w.qC[ci], n, w.qC[ni], &w.cnt[C_C0 + ni], gray, tid, nthreads);
+            if (tr) w.trace[level * 6 + 3] = gtimer();
+            waveC_phase2(m, h, w, w.qC[ci], n, w.qC[ni], &w.cnt[C_C0 + ni], tid, nthreads);
+            if (tr) w.trace[level * 6 + 4] = gtimer();
             grid_barrier(w.barrier, gen);
+            if (tr) w.trace[level * 6 + 5] = gtimer();
         }
         if (tid == 0) w.cnt[C_LEVC] = level;
     }
@@ -442,7 +695,7 @@ __global__ void __launch_bounds__(256) k_waves(LocDev m, HashDev h, WaveDev w, i
 
 // UpdateHashBatch (unify_helper.cuh:448-523)
 template <int VEC>
-__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h)
+__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display)
 {
     const int nq = m.N / VEC;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
@@ -472,6 +725,7 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h)
             if (blk < 0) continue;
             size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
             h.coc_glb[vi] = gie_pack_coc(gie_id2wr(pid) + m.upvt);
+            if (display && h.dist_sq[vi] != dist) h.dirty[blk] = 1;   // unify_helper.cuh:510-520
             h.dist_sq[vi] = dist;
             m.edt[id] = sqrtf((float)dist);
             h.pair[vi] = pr;
@@ -493,6 +747,13 @@ WaveDev make_wave_dev(gie_hashmap *hm)
     w.cseed_key = hm->cseed_key; w.cap = hm->queue_cap; w.cnt = hm->counters; w.barrier = hm->barrier;
     w.dec_dist = hm->decA_dist; w.dec_coc = hm->decA_coc; w.dec_pair = hm->decA_pair; w.dec_flags = hm->decA_flags;
     w.snap_id = hm->snap_id;
+    w.trace = hm->wave_trace;
+    w.cluster_size = hm->wave_cluster;
+    // enter the local mode when the frontier fits comfortably; leave it when the queues are more than half full
+    w.local_enter = hm->wave_cluster * LQ_CAP / 4;
+    w.local_spill = hm->wave_cluster * LQ_CAP / 2;
+    if (getenv("GIE_WAVE_NO_LOCAL")) w.local_enter = 0;
+
     return w;
 }
 
@@ -510,29 +771,54 @@ int gie_wave_prepare(gie_hashmap *hm)
     for (int i = 0; i < 3; i++) {
         GIE_CUDA_CHECK(cudaMalloc(&hm->qA[i], cap * 8));
         GIE_CUDA_CHECK(cudaMalloc(&hm->qB[i], cap * 8));
-        GIE_CUDA_CHECK(cudaMalloc(&hm->qC[i], cap * 4));
+        GIE_CUDA_CHECK(cudaMalloc(&hm->qC[i], cap * 8));
     }
     GIE_CUDA_CHECK(cudaMalloc(&hm->cseed_key, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->counters, C_COUNT * sizeof(int)));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, sizeof(unsigned int)));
+    int per_sm = 0;
+    GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_waves, WAVE_THREADS, 0));
+    if (per_sm < 1) { gie_set_error("wave kernel does not fit on an SM"); return GIE_ERR_CUDA; }
+    hm->wave_ctas = lm->num_sms;
+    hm->wave_cluster = 1;
+    // one CTA per SM in clusters of 16 (non-portable size) or 8 when the device can keep such a grid co-resident
+    // (cooperative launch); GIE_WAVE_CLUSTER overrides the size, 1 disables clusters
+    {
+        int want = getenv("GIE_WAVE_CLUSTER") ? atoi(getenv("GIE_WAVE_CLUSTER")) : 16;
+        for (int cs = want; cs >= 2; cs >>= 1) {
+            if (cs > 8 && cudaFuncSetAttribute(k_waves, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); continue; }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(WAVE_THREADS);
+            cudaLaunchAttribute attr;
+            attr.id = cudaLaunchAttributeClusterDimension; attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (void *)k_waves, &cfg) == cudaSuccess && nclusters >= 1) {
+                hm->wave_cluster = cs;
+                hm->wave_ctas = std::min(nclusters * cs, (lm->num_sms / cs) * cs);
+                break;
+            }
+            cudaGetLastError();
+        }
+    }
+    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, (size_t)(hm->wave_ctas + 1) * 32 * sizeof(unsigned int)));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_dist, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_coc, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_pair, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_flags, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->snap_id, cap * 4));
-    int per_sm = 0;
-    GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_waves, 256, 0));
-    if (per_sm < 1) { gie_set_error("wave kernel does not fit on an SM"); return GIE_ERR_CUDA; }
-    if (per_sm > 2) per_sm = 2;
-    hm->wave_ctas = per_sm * lm->num_sms;
+    if (getenv("GIE_WAVE_TRACE")) {
+        GIE_CUDA_CHECK(cudaMalloc(&hm->wave_trace, (size_t)TRACE_LEVELS * 10 * 8));
+        GIE_CUDA_CHECK(cudaMemset(hm->wave_trace, 0, (size_t)TRACE_LEVELS * 10 * 8));
+    }
     return GIE_OK;
 }
 
-int gie_launch_merge(gie_hashmap *hm, int map_ct)
+int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
 {
     gie_locmap *lm = hm->lm;
     const LocDev &m = lm->d;
     WaveDev w = make_wave_dev(hm);
+    w.display = display;
     const int vec = (m.X % 4 == 0) ? 4 : 1;
     long long groups = (long long)m.N / vec;
     long long want = (groups + 255) / 256, cap = (long long)lm->num_sms * 16;
@@ -540,7 +826,7 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct)
     {
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->counters, 0, C_COUNT * sizeof(int), lm->stream));
-        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, sizeof(unsigned int), lm->stream));
+        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, (size_t)(hm->wave_ctas + 1) * 32 * sizeof(unsigned int), lm->stream));
         if (vec == 4) {
             k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
             k_frontiers<4><<<grid, 256, 0, lm->stream>>>(m, hm->d, w, map_ct);
@@ -553,12 +839,30 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct)
         StageTimer t(lm, GIE_ST_WAVES);
         LocDev md = m; HashDev hd = hm->d; int ct = map_ct;
         void *args[] = { &md, &hd, &w, &ct };
-        GIE_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_waves, dim3(hm->wave_ctas), dim3(256), args, 0, lm->stream));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(hm->wave_ctas); cfg.blockDim = dim3(WAVE_THREADS); cfg.stream = lm->stream;
+        cudaLaunchAttribute attrs[2];
+        attrs[0].id = cudaLaunchAttributeCooperative; attrs[0].val.cooperative = 1;
+        attrs[1].id = cudaLaunchAttributeClusterDimension;
+        attrs[1].val.clusterDim.x = hm->wave_cluster; attrs[1].val.clusterDim.y = 1; attrs[1].val.clusterDim.z = 1;
+        cfg.attrs = attrs; cfg.numAttrs = hm->wave_cluster > 1 ? 2 : 1;
+        cudaError_t le = cudaLaunchKernelExC(&cfg, (void *)k_waves, args);
+        if (le != cudaSuccess && hm->wave_cluster > 1) {
+            // cooperative + cluster launch refused by this driver: fall back to single-CTA "clusters" for good
+            cudaGetLastError();
+            hm->wave_cluster = 1;
+            hm->wave_ctas = lm->num_sms;
+            w = make_wave_dev(hm);
+            w.display = display;
+            cfg.gridDim = dim3(hm->wave_ctas); cfg.numAttrs = 1;
+            le = cudaLaunchKernelExC(&cfg, (void *)k_waves, args);
+        }
+        GIE_CUDA_CHECK(le);
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        if (vec == 4) k_commit<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
-        else k_commit<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+        if (vec == 4) k_commit<4><<<grid, 256, 0, lm->stream>>>(m, hm->d, display);
+        else k_commit<1><<<grid, 256, 0, lm->stream>>>(m, hm->d, display);
     }
     k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->stats_host);
     lm->launches += 5;

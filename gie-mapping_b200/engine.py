@@ -62,7 +62,9 @@ def load_library():
         "gie_ogm_scan2d_dev": [p, p, p, i, f, f, i, i], "gie_ogm_scan2d_host": [p, p, p, i, f, f, i, i],
         "gie_ogm_vlp16_dev": [p, p, p, i, i, f, f, f, f, i, i], "gie_ogm_vlp16_host": [p, p, p, i, i, f, f, f, f, i, i],
         "gie_ogm_depth_dev": [p, p, p, i, i, f, f, f, f, i, i, i], "gie_ogm_depth_host": [p, p, p, i, i, f, f, f, f, i, i, i],
-        "gie_hashmap_update_ogm": [p, i, i], "gie_edt_batch_update": [p], "gie_hashmap_merge_new_obsv": [p, i],
+        "gie_hashmap_update_ogm": [p, i, i, i, i, p, p, p], "gie_edt_batch_update": [p], "gie_hashmap_merge_new_obsv": [p, i, i],
+        "gie_hashmap_num_changed": [p, C.POINTER(i)], "gie_hashmap_stream_changed": [p, p, p, i, C.POINTER(i)],
+        "gie_make_projection": [p, p, p, p], "gie_locmap_set_projection": [p, p, p, p], "gie_locmap_calculate_pivots": [p, p],
         "gie_sync": [p], "gie_hashmap_num_blocks": [p, C.POINTER(i)], "gie_hashmap_export_blocks": [p, p, p, i],
         "gie_hashmap_wave_stats": [p, p], "gie_profile_enable": [p, i], "gie_profile_last": [p, p],
         "gie_launch_count": [p, C.POINTER(C.c_longlong)], "gie_warmup": [],
@@ -178,6 +180,7 @@ class GlbHashMap:
         self._lMap = loc_map
         self._h = C.c_void_p()
         _check(self.lib.gie_hashmap_create(C.byref(self._h), loc_map._h, bucket_max, block_max))
+        self.hash_table_H_std = {}   # block key -> GlbVoxel[512], filled by streamPipeline
 
     def close(self):
         if self._h:
@@ -237,12 +240,32 @@ class GlbHashMap:
 
     # --- per-frame stages --------------------------------------------------------------------------------------
     def updateHashOGM(self, input_pynt, map_ct, stream_glb_ogm=False, ext_obsv=None):
-        if ext_obsv is not None:
-            raise GieError("external-obstacle AABBs are not supported (deactivated in the reference, pre_map.cu:85)")
-        _check(self.lib.gie_hashmap_update_ogm(self._h, int(input_pynt), map_ct))
+        """ext_obsv: None or (ll float32 [n,3], ur float32 [n,3], activated uint8 [n]) — Ext_Obs_Wrapper's boxes."""
+        if ext_obsv is None:
+            _check(self.lib.gie_hashmap_update_ogm(self._h, int(input_pynt), map_ct, int(stream_glb_ogm), 0, None, None, None))
+        else:
+            ll = np.ascontiguousarray(ext_obsv[0], np.float32).reshape(-1, 3)
+            ur = np.ascontiguousarray(ext_obsv[1], np.float32).reshape(-1, 3)
+            act = np.ascontiguousarray(ext_obsv[2], np.uint8).reshape(-1)
+            _check(self.lib.gie_hashmap_update_ogm(self._h, int(input_pynt), map_ct, int(stream_glb_ogm), ll.shape[0],
+                                                   _hostptr(ll), _hostptr(ur), _hostptr(act)))
 
     def mergeNewObsv(self, map_ct, display_glb_edt=False):
-        _check(self.lib.gie_hashmap_merge_new_obsv(self._h, map_ct))
+        _check(self.lib.gie_hashmap_merge_new_obsv(self._h, map_ct, int(display_glb_edt)))
+
+    def streamPipeline(self):
+        """GlbHashMap::streamPipeline: (keys int32 [n,3], voxels GLBVOXEL_DTYPE [n,512]) of the blocks changed since the
+        last call; merges them into the host mirror VB_keys_H / VB_values_H / hash_table_H_std."""
+        n = C.c_int()
+        _check(self.lib.gie_hashmap_num_changed(self._h, C.byref(n)))
+        keys = np.zeros((n.value, 3), np.int32)
+        vox = np.zeros((n.value, 512), dtype=GLBVOXEL_DTYPE)
+        if n.value:
+            _check(self.lib.gie_hashmap_stream_changed(self._h, _hostptr(keys), _hostptr(vox), n.value, C.byref(n)))
+            keys, vox = keys[:n.value], vox[:n.value]
+        for k, v in zip(keys.tolist(), vox):
+            self.hash_table_H_std[tuple(k)] = v
+        return keys, vox
 
     def sync(self):
         _check(self.lib.gie_sync(self._h))
@@ -317,12 +340,13 @@ class Mapper:
                 hm.ogm_depth(frame["depth"], cp["cx"], cp["cy"], cp["fx"], cp["fy"], cp.get("valid_NaN", True), fmp, r2)
         else:
             raise GieError(f"unknown sensor {s}")
-        hm.updateHashOGM(s == "pointcloud", self._time)
+        hm.updateHashOGM(s == "pointcloud", self._time, cfg.get("display_glb_ogm", False) and not cfg.get("display_glb_edt", False),
+                         frame.get("ext_obs"))
 
     def update_edt(self):
         """EDT half of publishMap: batchEDTUpdate + mergeNewObsv."""
         self.loc_map.batchEDTUpdate()
-        self.hash_map.mergeNewObsv(self._time)
+        self.hash_map.mergeNewObsv(self._time, self.cfg.get("display_glb_edt", False))
 
     def publishMap(self, frame, device_input=None):
         self.integrate(frame, device_input)

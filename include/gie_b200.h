@@ -62,7 +62,8 @@ typedef struct gie_glbvoxel {
     int32_t coc_glb[3];
     int32_t dist_sq;
     int32_t wave_layer;
-    uint64_t dist_id_pair; /* (dist_sq << 32) | wave-range coc id; the reference stores the two words swapped */
+    uint64_t dist_id_pair; /* Dist_id union (local_batch.h:26-30): low word sq_dist[0] = dist_sq, high word
+                              parent_loc_id[1] = wave-range coc id (11/11/10 bit) */
 } gie_glbvoxel;
 
 const char *gie_last_error(void);
@@ -135,13 +136,26 @@ int gie_ogm_depth_dev(gie_locmap *lm, gie_hashmap *hm, const float *depth_dev, i
 int gie_ogm_depth_host(gie_locmap *lm, gie_hashmap *hm, const float *depth_host, int rows, int cols, float cx,
                        float cy, float fx, float fy, int valid_nan, int for_motion_planner, int rbt_r2_grids);
 
-/* GlbHashMap::updateHashOGM (glb_hash_map.cu:115-143) incl. allocHashTB (:58-113).  External-obstacle AABBs
- * (Ext_Obs_Wrapper) are not supported: the reference ships them deactivated (src/kernel/pre_map/pre_map.cu:85). */
-int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct);
+/* GlbHashMap::updateHashOGM (glb_hash_map.cu:115-143) incl. allocHashTB (:58-113).
+ *   stream_glb_ogm : record blocks whose voxel type changed, for gie_hashmap_stream_changed (unify_helper.cuh:103-113)
+ *   n_obs, obs_*   : Ext_Obs_Wrapper's boxes (include/map_structure/pre_map.h:12-28), host arrays float[3*n_obs] lower-left /
+ *                    upper-right corners in metres and unsigned char[n_obs] activation flags; box 0 is the outer fence
+ *                    (voxels OUTSIDE it become obstacles), boxes 1.. are obstacles inside (unify_helper.cuh:68-86,149-162).
+ *                    n_obs = 0 or no activated box = the reference's shipped default (pre_map.cu:85). */
+int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream_glb_ogm, int n_obs,
+                           const float *obs_ll_host, const float *obs_ur_host, const unsigned char *obs_activated_host);
 /* EDT_OCC::batchEDTUpdate (src/kernel/edt/local_edt.cu:7-28); cuTT plans are not needed */
 int gie_edt_batch_update(gie_locmap *lm);
-/* GlbHashMap::mergeNewObsv (glb_hash_map.cu:146-207) */
-int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct);
+/* GlbHashMap::mergeNewObsv (glb_hash_map.cu:146-207).  display_glb_edt: record blocks whose distances changed
+ * (wave_core.cuh:128-134,250-256; unify_helper.cuh:510-520) for gie_hashmap_stream_changed. */
+int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt);
+/* GlbHashMap::streamPipeline + streamD2H (glb_hash_map.cu:209-247): the blocks recorded as changed since the last call,
+ * gathered on the device into the reference's GlbVoxel layout and copied with ONE device->host transfer (the reference
+ * issues one blocking 20 KB copy per block).  keys_host = int[3*max_blocks], voxels_host = gie_glbvoxel[512*max_blocks];
+ * *n_out blocks are returned and un-flagged; blocks that did not fit stay flagged.  gie_hashmap_num_changed = how many
+ * are pending. */
+int gie_hashmap_num_changed(gie_hashmap *hm, int *n);
+int gie_hashmap_stream_changed(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel *voxels_host, int max_blocks, int *n_out);
 /* waits for the stream and returns the sticky device-side status (queue overflow, out of blocks) */
 int gie_sync(gie_hashmap *hm);
 
@@ -161,6 +175,10 @@ int gie_profile_enable(gie_locmap *lm, int on);
 int gie_profile_last(gie_locmap *lm, float ms_out[GIE_ST_COUNT]);
 /* number of kernels this library launched since creation */
 int gie_launch_count(gie_locmap *lm, long long *n);
+
+/* diagnostics: per wave-C BFS level {frontier size, 5 globaltimer stamps in ns}; only when the map was created with the
+ * environment variable GIE_WAVE_TRACE set.  out = uint64[6 * max_levels] */
+int gie_debug_wave_trace(gie_hashmap *hm, unsigned long long *out, int max_levels);
 
 /* warmupCuda (include/warmup.h:9) */
 int gie_warmup(void);

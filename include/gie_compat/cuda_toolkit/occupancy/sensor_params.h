@@ -1,6 +1,7 @@
 // Sensor parameter PODs of the four OGM front ends (reference: include/cuda_toolkit/occupancy/*/{pntcld,scan,multiscan,
 // camera}_param.h).  Member names and constructor argument order follow the reference so call sites compile unchanged.
 #pragma once
+#include <vector_types.h>
 struct PntcldParam {
     int cld_sz = 0, valid_pnt_count = 0;
     PntcldParam() = default;

@@ -42,6 +42,9 @@ def lib():
         l.gor_batch_edt_bruteforce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.gor_merge_new_obsv.argtypes = [C.c_void_p, C.c_int]
         l.gor_get_pivots.argtypes = [C.c_void_p, C.c_void_p]
+        l.gor_set_ext_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.gor_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        l.gor_take_changed.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         l.gor_num_blocks.argtypes = [C.c_void_p]
         l.gor_export_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         l.gor_cuda_atan2f.restype = C.c_float
@@ -124,6 +127,16 @@ class OracleMapper:
                                  int(cp.get("valid_NaN", True)), fmp, r2)
         else:
             raise KeyError(s)
+        self.l.gor_set_stream(self.h, int(cfg.get("display_glb_ogm", False) and not cfg.get("display_glb_edt", False)),
+                              int(cfg.get("display_glb_edt", False)))
+        eo = frame.get("ext_obs")
+        if eo is not None:
+            ll = np.ascontiguousarray(eo[0], np.float32).reshape(-1, 3)
+            ur = np.ascontiguousarray(eo[1], np.float32).reshape(-1, 3)
+            act = np.ascontiguousarray(eo[2], np.uint8).reshape(-1)
+            self.l.gor_set_ext_obs(self.h, ll.shape[0], _p(ll), _p(ur), _p(act))
+        else:
+            self.l.gor_set_ext_obs(self.h, 0, None, None, None)
         self.l.gor_update_hash_ogm(self.h, int(s == "pointcloud"), self._time)
 
     def batch_edt(self):
@@ -137,12 +150,23 @@ class OracleMapper:
         self.integrate(frame)
         self.update_edt()
 
+    def take_changed(self):
+        """Block keys recorded as changed since the last call (streamPipeline's key set), int32 [n,3]."""
+        n = self.l.gor_take_changed(self.h, None, 0)
+        keys = np.zeros((n, 3), np.int32)
+        if n:
+            self.l.gor_take_changed(self.h, _p(keys), n)
+        return keys
+
     def export_blocks(self):
+        """Blocks in the reference layout; dist_id_pair in the reference's word order (low word = dist_sq)."""
         n = self.l.gor_num_blocks(self.h)
         keys = np.zeros((n, 3), np.int32)
         vox = np.zeros((n, 512), dtype=GVOX_DTYPE)
         if n:
             self.l.gor_export_blocks(self.h, _p(keys), _p(vox))
+            p = vox["dist_id_pair"]
+            vox["dist_id_pair"] = (p >> np.uint64(32)) | (p << np.uint64(32))
         return keys, vox
 
 

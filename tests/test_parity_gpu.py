@@ -127,3 +127,88 @@ def test_batch_edt_large_property(gie):
     from scipy import ndimage
     ref = ndimage.distance_transform_edt(t != 2) ** 2
     assert np.array_equal(np.rint(ref).astype(np.int64), d)
+
+
+def test_external_obstacles_and_fence(gie, oracle):
+    """Ext_Obs_Wrapper boxes (unify_helper.cuh:68-86,149-162): obstacle boxes inside the volume and the outer fence (box 0),
+    on the ray-cast and on a projective sensor path."""
+    for name in ["cfg4", "cfg3"]:
+        cfg = gie.scenes.small_config(name, (48, 48, 24), cutoff_grids_sq=64)
+        frames = gie.scenes.make_frames(cfg, 5, dynamic=True)
+        mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+        try:
+            for k, f in enumerate(frames):
+                f = dict(f)
+                org = (np.floor(np.asarray(f["t"], np.float32) / cfg["voxel_width"] + 0.5) - np.array(cfg["local_size"]) // 2) * cfg["voxel_width"]
+                ll = np.stack([org + 0.4, org + 1.0, org + 3.0]).astype(np.float32)
+                ur = np.stack([org + 4.2, org + 1.9, org + 3.5]).astype(np.float32)
+                act = np.array([k >= 3, k >= 1, k % 2 == 0], np.uint8)   # fence switches on at frame 3
+                f["ext_obs"] = (ll, ur, act)
+                mp.publishMap(f)
+                om.publishMap(f)
+                _cmp_frame(gie, mp, om, f"{name} ext-obs frame {k}")
+            _cmp_blocks(mp, om, name)
+        finally:
+            mp.close()
+            om.close()
+
+
+def test_stream_pipeline_matches_oracle(gie, oracle):
+    """GlbHashMap::streamPipeline: the set of changed blocks per frame and the streamed voxel contents."""
+    for flags in [dict(display_glb_edt=True), dict(display_glb_ogm=True)]:
+        cfg = gie.scenes.small_config("cfg4", (48, 48, 24), cutoff_grids_sq=64)
+        cfg.update(flags)
+        frames = gie.scenes.make_frames(cfg, 6, dynamic=True)
+        mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+        try:
+            for k, f in enumerate(frames):
+                mp.publishMap(f)
+                om.publishMap(f)
+                keys, vox = mp.hash_map.streamPipeline()
+                okeys = om.take_changed()
+                assert sorted(map(tuple, keys.tolist())) == sorted(map(tuple, okeys.tolist())), f"{flags} frame {k}: changed set"
+                ok, ov = om.export_blocks()
+                lut = {tuple(kk): i for i, kk in enumerate(ok.tolist())}
+                for kk, v in zip(keys.tolist(), vox):
+                    o = ov[lut[tuple(kk)]]
+                    for field in ["occ_val", "vox_type", "coc_glb", "dist_sq", "dist_id_pair", "update_ct", "wave_layer"]:
+                        assert np.array_equal(v[field], o[field]), f"{flags} frame {k} block {kk}: {field}"
+            assert len(mp.hash_map.hash_table_H_std) > 0
+            assert mp.hash_map.streamPipeline()[0].shape[0] == 0   # nothing pending after a take
+        finally:
+            mp.close()
+            om.close()
+
+
+@pytest.mark.parametrize("name,size,cutoff", [("cfg4", (48, 48, 24), 64), ("cfg1", (64, 64, 16), 100), ("cfg2", (64, 64, 32), 49),
+                                              ("cfg3", (64, 64, 32), 100)])
+def test_cpp_host_replay_parity(gie, oracle, tmp_path, name, size, cutoff):
+    """The C++ host driver (reference operator surface from include/gie_compat over the C ABI) against the oracle, frame by
+    frame, plus the host mirror of the global map that streamPipeline maintains and the CostMap payload."""
+    cfg = gie.scenes.small_config(name, size, cutoff_grids_sq=cutoff)
+    frames = gie.scenes.make_frames(cfg, 5, dynamic=True)
+    out, mirror, _ = gie.replay_io.run_replay(cfg, frames, str(tmp_path), stream=True, costmap=True)
+    cfg_o = dict(cfg); cfg_o["display_glb_edt"] = True
+    om = oracle.OracleMapper(cfg_o)
+    omirror = {}
+    try:
+        for k, f in enumerate(frames):
+            om.publishMap(f)
+            r = out[k]
+            assert np.array_equal(r["glb_type"], om.glb_type), f"frame {k} glb_type"
+            assert np.array_equal(r["aux"], om.aux) and np.array_equal(r["coc_aux"], om.coc_aux), f"frame {k} batch EDT"
+            assert np.array_equal(r["pair"], om.pair), f"frame {k} pair"
+            known = om.glb_type != 0
+            assert np.array_equal(r["edt"][known].view(np.uint32), om.edt[known].view(np.uint32)), f"frame {k} edt"
+            assert np.array_equal(r["costmap"]["d"].view(np.uint32), r["edt"].view(np.uint32))
+            assert np.array_equal(r["costmap"]["o"] != 0, om.glb_type != 0)
+            ok, ov = om.export_blocks()
+            lut = {tuple(kk): i for i, kk in enumerate(ok.tolist())}
+            for kk in om.take_changed().tolist():
+                omirror[tuple(kk)] = ov[lut[tuple(kk)]].copy()
+        assert set(mirror) == set(omirror)
+        for kk, v in mirror.items():
+            for field in ["occ_val", "vox_type", "coc_glb", "dist_sq", "dist_id_pair"]:
+                assert np.array_equal(v[field], omirror[kk][field]), f"mirror block {kk}: {field}"
+    finally:
+        om.close()
