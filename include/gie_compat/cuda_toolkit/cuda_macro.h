@@ -28,3 +28,24 @@ inline void check(int status, const char *where)
 }
 }  // namespace gie
 #define GIE_CHECK(call) ::gie::check((call), #call)
+
+// The device-memory helpers the reference's ROS-typed MapMakers use for their sensor staging buffers
+// (src/*_map_maker.cpp: GPU_MALLOC / GPU_MEMCPY_H2D / GPU_FREE) and the node's profiling sync (volumetric_mapper.cpp:186).
+#include <cuda_runtime_api.h>
+namespace gie {
+inline void cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return;
+    std::fprintf(stderr, "CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+    std::exit(1);
+}
+}  // namespace gie
+#define GPU_MALLOC(ptr, bytes) ::gie::cuda_ok(cudaMalloc((void **)(ptr), (bytes)), "GPU_MALLOC")
+#define GPU_FREE(ptr) ::gie::cuda_ok(cudaFree(ptr), "GPU_FREE")
+#define GPU_MEMSET(ptr, v, bytes) ::gie::cuda_ok(cudaMemset((ptr), (v), (bytes)), "GPU_MEMSET")
+#define GPU_MEMCPY_H2D(d, s, bytes) ::gie::cuda_ok(cudaMemcpy((d), (s), (bytes), cudaMemcpyHostToDevice), "GPU_MEMCPY_H2D")
+#define GPU_MEMCPY_D2H(d, s, bytes) ::gie::cuda_ok(cudaMemcpy((d), (s), (bytes), cudaMemcpyDeviceToHost), "GPU_MEMCPY_D2H")
+#define GPU_MEMCPY_D2D(d, s, bytes) ::gie::cuda_ok(cudaMemcpy((d), (s), (bytes), cudaMemcpyDeviceToDevice), "GPU_MEMCPY_D2D")
+#define GPU_DEV_SYNC() ::gie::cuda_ok(cudaDeviceSynchronize(), "GPU_DEV_SYNC")
+#define SENS_FAR_DIST 1000.f
+#define GPU_PI_FLOAT 3.1415926f

@@ -29,4 +29,5 @@ struct CamParam {
 };
 typedef float SCAN_DEPTH_TPYE;        // spelling as in the reference
 typedef float REALSENSE_DEPTH_TPYE;
+typedef float LASER_RANGE_TPYE;
 typedef float3 PNT_TYPE;

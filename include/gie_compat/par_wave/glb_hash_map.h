@@ -3,6 +3,7 @@
 #pragma once
 #include <unordered_map>
 #include <vector>
+#include <thrust/detail/raw_pointer_cast.h>   // the node wraps VB_keys_loc_D.data() in thrust::raw_pointer_cast
 #include "par_wave/voxmap_utils.cuh"
 #include "map_structure/pre_map.h"
 
