@@ -212,3 +212,89 @@ def test_cpp_host_replay_parity(gie, oracle, tmp_path, name, size, cutoff):
                 assert np.array_equal(v[field], omirror[kk][field]), f"mirror block {kk}: {field}"
     finally:
         om.close()
+
+
+def _check_frame_invariants(gie, mp, cfg, tag):
+    """Size-independent properties of one merged frame (no oracle needed): see test_full_size_properties."""
+    lm = mp.loc_map
+    X, Y, Z = cfg["local_size"]
+    t = lm.download(gie.ARR_GLB_TYPE)
+    pair = lm.download(gie.ARR_PAIR)
+    aux = lm.download(gie.ARR_AUX)
+    edt = lm.download(gie.ARR_EDT)
+    pvt, upvt, _ = lm.pivots()
+    dist = (pair >> np.uint64(32)).astype(np.int64)
+    pid = (pair & np.uint64(0xffffffff)).astype(np.int64)
+    known = t != 0
+    valid = known & (dist < 900000)
+    assert valid.sum() > 0, tag
+    # closest-obstacle coordinate of every valid voxel, in local coordinates (may lie outside the volume)
+    zz, yy, xx = np.nonzero(valid)
+    p = pid[valid]
+    cx = (p & 0x7ff) + upvt[0] - pvt[0]
+    cy = ((p >> 11) & 0x7ff) + upvt[1] - pvt[1]
+    cz = ((p >> 22) & 0x3ff) + upvt[2] - pvt[2]
+    d = dist[valid]
+    assert np.array_equal((xx - cx) ** 2 + (yy - cy) ** 2 + (zz - cz) ** 2, d), f"{tag}: dist != |voxel - coc|^2"
+    inside = (cx >= 0) & (cx < X) & (cy >= 0) & (cy < Y) & (cz >= 0) & (cz < Z)
+    assert (t[cz[inside], cy[inside], cx[inside]] == 2).all(), f"{tag}: an in-volume coc is not OCCUPIED"
+    occ = t == 2
+    assert (dist[occ] == 0).all(), f"{tag}: occupied voxel with non-zero distance"
+    assert (d[t[valid] != 2] > 0).all(), tag
+    a = aux[valid]
+    assert (d[a < 900000] <= a[a < 900000]).all(), f"{tag}: merge raised a distance"
+    assert np.array_equal(edt[valid].view(np.uint32), np.sqrt(d.astype(np.float32)).view(np.uint32)), f"{tag}: edt != sqrtf(dist)"
+    return int(known.sum()), int(occ.sum())
+
+
+@pytest.mark.parametrize("name,nframes", [("cfg4", 6), ("cfg2", 4), ("cfg3", 3), ("cfg1", 4)])
+def test_full_size_properties(gie, name, nframes):
+    """BASELINE.json configurations at their FULL sizes (cfg4 512^3 headline, cfg2/cfg3 256^3, cfg1 128x128x32): invariants of
+    the merged map that hold at any size — dist == |voxel - coc|^2, in-volume cocs are OCCUPIED, occupied voxels have
+    distance 0, the merge never raises a batch distance, edt == sqrtf(dist) bit-exactly, no device-side error — plus
+    idempotence: integrating nothing new and re-running the EDT half leaves the committed pairs unchanged."""
+    cfg = gie.scenes.make_config(name)
+    frames = gie.scenes.make_frames(cfg, nframes)
+    mp = gie.Mapper(cfg)
+    try:
+        seen = []
+        for k, f in enumerate(frames):
+            mp.publishMap(f)
+            mp.hash_map.sync()
+            if k >= nframes - 2:
+                seen.append(_check_frame_invariants(gie, mp, cfg, f"{name} frame {k}"))
+        assert seen[-1][1] > 0, "no obstacle was mapped"
+        before = mp.loc_map.download(gie.ARR_PAIR).copy()
+        mp.update_edt()            # same occupancy, same pose: batch EDT + merge again
+        mp.hash_map.sync()
+        after = mp.loc_map.download(gie.ARR_PAIR)
+        known = mp.loc_map.download(gie.ARR_GLB_TYPE) != 0
+        assert np.array_equal(before[known], after[known]), "re-running the EDT half changed committed distances"
+    finally:
+        mp.close()
+
+
+def test_batch_edt_headline_size_vs_scipy(gie):
+    """512^3 (the headline volume): squared distances exactly equal to scipy's exact EDT; coc consistency."""
+    from scipy import ndimage
+    X = Y = Z = 512
+    rng = np.random.RandomState(11)
+    t = np.ones((Z, Y, X), np.int8)
+    idx = rng.randint(0, X, size=(20000, 3))
+    t[idx[:, 2] // 2 + 100, idx[:, 1], idx[:, 0]] = 2      # obstacles only in 256 of the 512 slices: exercises slice skipping
+    lm = gie.LocMap(0.1, (X, Y, Z), cutoff_grids_sq=2500)
+    try:
+        lm.upload_glb_type(t)
+        lm.batchEDTUpdate()
+        d = lm.download(gie.ARR_AUX)
+        c = lm.download(gie.ARR_COC_AUX)
+    finally:
+        lm.close()
+    ref = ndimage.distance_transform_edt(t != 2)
+    ref2 = np.rint(ref * ref).astype(np.int32)
+    assert np.array_equal(ref2, d)
+    cx, cy, cz = c & 0x7ff, (c >> 11) & 0x7ff, (c >> 22) & 0x3ff
+    assert (t[cz, cy, cx] == 2).all()
+    sl = slice(None, None, 7)   # coc consistency on a strided subset (memory)
+    zz, yy, xx = np.meshgrid(np.arange(Z)[sl], np.arange(Y)[sl], np.arange(X)[sl], indexing="ij")
+    assert np.array_equal((xx - cx[sl, sl, sl]) ** 2 + (yy - cy[sl, sl, sl]) ** 2 + (zz - cz[sl, sl, sl]) ** 2, d[sl, sl, sl])
