@@ -407,6 +407,58 @@ int gie_ogm_depth_host(gie_locmap *lm, gie_hashmap *hm, const float *img, int ro
     return gie_launch_ogm_depth(lm, hm, lm->stage_dev, rows, cols, cx, cy, fx, fy, valid_nan, fmp, r2);
 }
 
+// ---- raw PointCloud2 front ends ----------------------------------------------------------------------
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int gie_ogm_vlp16_pointcloud2_host(gie_locmap *lm, gie_hashmap *hm, const void *data, int n_points, int point_step, int off_x, int off_y,
+                                   int off_ring, int scan_num, int ring_num, float tinc, float tmin, float pinc, float pmin, int fmp, int r2)
+{
+    int rc = check_frame_args(lm, hm);
+    if (rc != GIE_OK) return rc;
+    if (n_points < 0 || (n_points > 0 && !data) || point_step < 1 || off_x < 0 || off_y < 0 || off_ring < 0 || off_x + 4 > point_step ||
+        off_y + 4 > point_step || off_ring + 2 > point_step || scan_num < 1 || ring_num < 1 || tinc == 0.f || pinc == 0.f) {
+        gie_set_error("bad PointCloud2 layout");
+        return GIE_ERR_INVALID_ARG;
+    }
+    const size_t raw = align256((size_t)n_points * point_step), cells = (size_t)scan_num * ring_num;
+    if ((rc = ensure_stage(lm, raw + align256(cells * 8) + cells * 4 + 256)) != GIE_OK) return rc;
+    unsigned char *raw_dev = (unsigned char *)lm->stage_dev;
+    unsigned long long *img = (unsigned long long *)(raw_dev + raw);
+    float *ranges = (float *)(raw_dev + raw + align256(cells * 8));
+    if (n_points) GIE_CUDA_CHECK(cudaMemcpyAsync(raw_dev, data, (size_t)n_points * point_step, cudaMemcpyHostToDevice, lm->stream));
+    if ((rc = gie_launch_vlp16_bin(lm, raw_dev, n_points, point_step, off_x, off_y, off_ring, scan_num, ring_num, tinc, img, ranges)) != GIE_OK) return rc;
+    return gie_launch_ogm_vlp16(lm, hm, ranges, scan_num, ring_num, tinc, tmin, pinc, pmin, fmp, r2);
+}
+
+int gie_vlp16_last_ranges(gie_locmap *lm, int n_points, int point_step, int scan_num, int ring_num, float *ranges_host)
+{
+    if (!lm || !ranges_host || !lm->stage_dev) return GIE_ERR_INVALID_ARG;
+    const size_t raw = align256((size_t)n_points * point_step), cells = (size_t)scan_num * ring_num;
+    if (lm->stage_bytes < raw + align256(cells * 8) + cells * 4) return GIE_ERR_INVALID_ARG;
+    GIE_CUDA_CHECK(cudaMemcpyAsync(ranges_host, (char *)lm->stage_dev + raw + align256(cells * 8), cells * 4, cudaMemcpyDeviceToHost, lm->stream));
+    GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream));
+    return GIE_OK;
+}
+
+int gie_ogm_pointcloud2_host(gie_locmap *lm, gie_hashmap *hm, const void *data, int n_points, int point_step, int off_x, int max_points,
+                             int fmp, int r2)
+{
+    int rc = check_frame_args(lm, hm);
+    if (rc != GIE_OK) return rc;
+    if (n_points < 0 || (n_points > 0 && !data) || point_step < 12 || off_x < 0 || off_x + 12 > point_step) {
+        gie_set_error("bad PointCloud2 layout");
+        return GIE_ERR_INVALID_ARG;
+    }
+    const int n = (max_points > 0 && n_points > max_points) ? max_points : n_points;   // cld_sz cap, pntcld_map_maker.cpp:55
+    const size_t raw = align256((size_t)n * point_step);
+    if ((rc = ensure_stage(lm, raw + (size_t)n * 12 + 256)) != GIE_OK) return rc;
+    unsigned char *raw_dev = (unsigned char *)lm->stage_dev;
+    float *pts = (float *)(raw_dev + raw);
+    if (n) GIE_CUDA_CHECK(cudaMemcpyAsync(raw_dev, data, (size_t)n * point_step, cudaMemcpyHostToDevice, lm->stream));
+    if ((rc = gie_launch_pc_repack(lm, raw_dev, n, point_step, off_x, pts)) != GIE_OK) return rc;
+    return gie_launch_ogm_pointcloud(lm, hm, pts, n, fmp, r2);
+}
+
 // ---- per-frame stages -----------------------------------------------------------------------------------------------
 int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream_glb_ogm, int n_obs, const float *obs_ll,
                            const float *obs_ur, const unsigned char *obs_activated)

@@ -52,6 +52,7 @@ struct gie_hashmap {
     int32_t *decA_flags = nullptr;
     uint32_t *snap_id = nullptr;  // per-queue-slot snapshot for waves B/C
     int wave_ctas = 0;
+    int merge_epoch = 0;          // merges done so far; the seed mark of m.wave_layer (memset to 0 at creation)
     int wave_cluster = 1;         // CTAs per thread-block cluster of the wave kernel
     unsigned long long *wave_trace = nullptr;   // diagnostics, allocated when GIE_WAVE_TRACE is set
     // external-obstacle boxes of the current frame: [n][7] = ll.xyz, ur.xyz, activated
@@ -87,6 +88,9 @@ int gie_launch_ogm_vlp16(gie_locmap *lm, gie_hashmap *hm, const float *ranges, i
                          float tmin, float pinc, float pmin, int fmp, int r2);
 int gie_launch_ogm_depth(gie_locmap *lm, gie_hashmap *hm, const float *img, int rows, int cols, float cx, float cy,
                          float fx, float fy, int valid_nan, int fmp, int r2);
+int gie_launch_vlp16_bin(gie_locmap *lm, const unsigned char *raw_dev, int n, int step, int off_x, int off_y, int off_ring,
+                         int scan_num, int ring_num, float theta_inc, unsigned long long *img_dev, float *ranges_dev);
+int gie_launch_pc_repack(gie_locmap *lm, const unsigned char *raw_dev, int n, int step, int off_x, float *pts_dev);
 // hashmap.cu
 int gie_hash_begin_frame(gie_hashmap *hm);                       // sets the table origin, clears touched flags
 int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int stream_glb_ogm, int n_obs);

@@ -86,83 +86,122 @@ __device__ __forceinline__ bool ext_obs_flag(const LocDev &m, int3 glb, int n_ob
 }
 
 template <bool PNTCLD, int VEC>
-__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs)
+__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
+                                                   int tpr_log2)
 {
-    const int nq = m.N / VEC;                       // X % VEC == 0, so a group never straddles a row
-    const int nq_pad = (nq + 31) & ~31;             // whole warps run the collective below
+    // A CTA pass covers 256 >> tpr_log2 rows (y,z) of the volume with 1 << tpr_log2 threads per row; everything that
+    // depends only on (y,z) — the block-table row, the voxel offset inside a block — is computed once per row, and all loop
+    // bounds are uniform so that the rare allocation path can use warp collectives.
+    const int gx = m.X / VEC;                        // X % VEC == 0: a group of VEC voxels never straddles a row
+    const int tpr = 1 << tpr_log2, rpc = 256 >> tpr_log2;
+    const int r_in = threadIdx.x >> tpr_log2, xg0 = threadIdx.x & (tpr - 1);
+    const int nrows = m.Y * m.Z;
     const int lane = threadIdx.x & 31;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq_pad; q += gridDim.x * blockDim.x) {
-        const bool valid = q < nq;
-        const int id0 = valid ? q * VEC : 0;
-        const int x0 = id0 % m.X, yz = id0 / m.X;
-        const int y = yz % m.Y, z = yz / m.Y;
-        int cnt[VEC];
-        int8_t inst[VEC], out_type[VEC];
-        if (VEC == 4) {
-            char4 i4 = valid ? *reinterpret_cast<const char4 *>(m.inst_type + id0) : make_char4(0, 0, 0, 0);
-            inst[0] = i4.x; inst[1] = i4.y; inst[2] = i4.z; inst[3] = i4.w;
-            int4 c4 = make_int4(0, 0, 0, 0);
-            if (PNTCLD && valid) c4 = *reinterpret_cast<const int4 *>(m.ray_count + id0);
-            cnt[0] = c4.x; cnt[1] = c4.y; cnt[2] = c4.z; cnt[3] = c4.w;
-        } else {
-            inst[0] = valid ? m.inst_type[id0] : 0;
-            cnt[0] = (PNTCLD && valid) ? m.ray_count[id0] : 0;
-        }
-        bool any_cnt = false, any_inst = false;
+    for (int row0 = blockIdx.x * rpc; row0 < nrows; row0 += gridDim.x * rpc) {
+        const int row = row0 + r_in;
+        const bool row_ok = row < nrows;
+        const int y = row_ok ? row % m.Y : 0, z = row_ok ? row / m.Y : 0;
+        const int gy = y + m.pvt.y, gz = z + m.pvt.z;
+        const int trow = (((gz >> 3) - h.tab_org.z) * h.tab_dim.y + ((gy >> 3) - h.tab_org.y)) * h.tab_dim.x - h.tab_org.x;
+        const int vrow = (gz & 7) * 64 + (gy & 7) * 8;
+        for (int xgb = 0; xgb < gx; xgb += tpr) {
+            const int xg = xgb + xg0;
+            const bool valid = row_ok && xg < gx;
+            const int x0 = xg * VEC;
+            const int id0 = valid ? row * m.X + x0 : 0;
+            const int gx0 = x0 + m.pvt.x;
+            int cnt[VEC], ti[VEC], blk[VEC];
+            int8_t inst[VEC], out_type[VEC];
+            if (VEC >= 4) {   // VEC consecutive voxels per thread: 16-byte loads of the counters, all issued before any use
 #pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            any_cnt |= cnt[k] != 0; any_inst |= inst[k] != GIE_VOX_UNKNOWN;
-            const bool observed = valid && (PNTCLD ? (cnt[k] != 0) : (inst[k] == GIE_VOX_OCCUPIED || inst[k] == GIE_VOX_FREE));
-            const int3 glb = make_int3(x0 + k, y, z) + m.pvt;
-            const int ti = gie_tab_index(h, glb);
-            int blk = __ldcg(&h.btab[ti]);
-            // warp-aggregated allocation: one lane per distinct missing block inserts, the others take its result
-            const bool need = blk < 0 && observed;
-            if (__any_sync(0xffffffffu, need)) {   // rare after the first frames: blocks already exist
-                unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
-                int leader = __ffs(grp) - 1;
-                int res = -1;
-                if (need && lane == leader) {
-                    res = hash_insert(h, gie_vb_key(glb));
-                    if (res >= 0) h.btab[ti] = res;
+                for (int v = 0; v < VEC; v += 4) {
+                    char4 i4 = valid ? *reinterpret_cast<const char4 *>(m.inst_type + id0 + v) : make_char4(0, 0, 0, 0);
+                    inst[v] = i4.x; inst[v + 1] = i4.y; inst[v + 2] = i4.z; inst[v + 3] = i4.w;
+                    int4 c4 = make_int4(0, 0, 0, 0);
+                    if (PNTCLD && valid) c4 = *reinterpret_cast<const int4 *>(m.ray_count + id0 + v);
+                    cnt[v] = c4.x; cnt[v + 1] = c4.y; cnt[v + 2] = c4.z; cnt[v + 3] = c4.w;
                 }
-                res = __shfl_sync(0xffffffffu, res, leader);
-                if (need) blk = res;
+            } else {
+                inst[0] = valid ? m.inst_type[id0] : 0;
+                cnt[0] = (PNTCLD && valid) ? m.ray_count[id0] : 0;
             }
-            int8_t type = GIE_VOX_UNKNOWN;
-            if (valid && blk >= 0) {
-                size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
-                type = h.vox_type[vi];
-                const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
-                if (observed || occ_flag) {
-                    const int8_t old_type = type;
-                    uint8_t occ = h.occ_val[vi];
-                    if (PNTCLD) {
-                        if (cnt[k] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
-                        else {
-                            float p = fminf(1.f, __fdiv_rn((float)(-cnt[k]), 10.f));
-                            set_occ_val(occ, type, 0.f, p, m.thresh);
-                        }
-                    } else {
-                        if (inst[k] == GIE_VOX_OCCUPIED || occ_flag) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
-                        else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
+            bool any_cnt = false, any_inst = false, any_need = false, any_blk = false;
+            bool observed[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; k++) {
+                any_cnt |= cnt[k] != 0; any_inst |= inst[k] != GIE_VOX_UNKNOWN;
+                observed[k] = valid && (PNTCLD ? (cnt[k] != 0) : (inst[k] == GIE_VOX_OCCUPIED || inst[k] == GIE_VOX_FREE));
+                ti[k] = trow + ((gx0 + k) >> 3);
+                if (k > 0 && ti[k] == ti[k - 1]) blk[k] = blk[k - 1];
+                else blk[k] = valid ? __ldcg(&h.btab[ti[k]]) : -1;
+                any_need |= observed[k] && blk[k] < 0;
+                any_blk |= blk[k] >= 0;
+            }
+            if (__any_sync(0xffffffffu, any_need)) {
+                // rare after the first frames.  Warp-aggregated allocation: one lane per distinct missing block inserts,
+                // the others take its result
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    bool need = observed[k] && blk[k] < 0;
+                    if (need) {   // a sibling voxel of this thread (or another warp) may have created the block meanwhile
+                        int b = __ldcg(&h.btab[ti[k]]);
+                        if (b >= 0) { blk[k] = b; need = false; }
                     }
-                    h.occ_val[vi] = occ;
-                    h.vox_type[vi] = type;
-                    if (stream && type != old_type) h.dirty[blk] = 1;
+                    unsigned grp = __match_any_sync(0xffffffffu, need ? ti[k] : -1);
+                    int leader = __ffs(grp) - 1;
+                    int res = -1;
+                    if (need && lane == leader) {
+                        res = hash_insert(h, make_int3((gx0 + k) >> 3, gy >> 3, gz >> 3));
+                        if (res >= 0) h.btab[ti[k]] = res;
+                    }
+                    res = __shfl_sync(0xffffffffu, res, leader);
+                    if (need) blk[k] = res;
+                    any_blk |= blk[k] >= 0;
                 }
             }
-            out_type[k] = type;
-        }
-        if (!valid) continue;
-        if (VEC == 4) {
-            if (any_cnt) *reinterpret_cast<int4 *>(m.ray_count + id0) = make_int4(0, 0, 0, 0);
-            if (any_inst) *reinterpret_cast<char4 *>(m.inst_type + id0) = make_char4(0, 0, 0, 0);
-            *reinterpret_cast<char4 *>(m.glb_type + id0) = make_char4(out_type[0], out_type[1], out_type[2], out_type[3]);
-        } else {
-            if (any_cnt) m.ray_count[id0] = 0;
-            if (any_inst) m.inst_type[id0] = GIE_VOX_UNKNOWN;
-            m.glb_type[id0] = out_type[0];
+            if (!valid) continue;
+#pragma unroll
+            for (int k = 0; k < VEC; k++) out_type[k] = GIE_VOX_UNKNOWN;
+            if (any_blk) {
+#pragma unroll
+                for (int k = 0; k < VEC; k++) {
+                    if (blk[k] < 0) continue;
+                    const int3 glb = make_int3(gx0 + k, gy, gz);
+                    size_t vi = (size_t)blk[k] * 512 + vrow + (glb.x & 7);
+                    int8_t type = h.vox_type[vi];
+                    const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
+                    if (observed[k] || occ_flag) {
+                        const int8_t old_type = type;
+                        uint8_t occ = h.occ_val[vi];
+                        if (PNTCLD) {
+                            if (cnt[k] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
+                            else {
+                                float p = fminf(1.f, __fdiv_rn((float)(-cnt[k]), 10.f));
+                                set_occ_val(occ, type, 0.f, p, m.thresh);
+                            }
+                        } else {
+                            if (inst[k] == GIE_VOX_OCCUPIED || occ_flag) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
+                            else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
+                        }
+                        h.occ_val[vi] = occ;
+                        h.vox_type[vi] = type;
+                        if (stream && type != old_type) h.dirty[blk[k]] = 1;
+                    }
+                    out_type[k] = type;
+                }
+            }
+            if (VEC >= 4) {
+#pragma unroll
+                for (int v = 0; v < VEC; v += 4) {
+                    if (any_cnt) *reinterpret_cast<int4 *>(m.ray_count + id0 + v) = make_int4(0, 0, 0, 0);
+                    if (any_inst) *reinterpret_cast<char4 *>(m.inst_type + id0 + v) = make_char4(0, 0, 0, 0);
+                    *reinterpret_cast<char4 *>(m.glb_type + id0 + v) = make_char4(out_type[v], out_type[v + 1], out_type[v + 2], out_type[v + 3]);
+                }
+            } else {
+                if (any_cnt) m.ray_count[id0] = 0;
+                if (any_inst) m.inst_type[id0] = GIE_VOX_UNKNOWN;
+                m.glb_type[id0] = out_type[0];
+            }
         }
     }
 }
@@ -272,21 +311,28 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     const float *obs = hm->obs_dev;
     gie_locmap *lm = hm->lm;
     StageTimer t(lm, GIE_ST_HASH_MERGE);
-    const int vec = (lm->d.X % 4 == 0) ? 4 : 1;
-    long long groups = (long long)lm->d.N / vec;
-    int grid = (int)std::min<long long>((groups + 255) / 256, (long long)lm->num_sms * 16);
+    const int vec = (lm->d.X % 8 == 0) ? 8 : (lm->d.X % 4 == 0) ? 4 : 1;
+    const int gx = lm->d.X / vec;
+    int tpr_log2 = 5;
+    while ((1 << tpr_log2) < gx && tpr_log2 < 8) tpr_log2++;
+    const int rpc = 256 >> tpr_log2;
+    const long long passes = ((long long)lm->d.Y * lm->d.Z + rpc - 1) / rpc;
+    int grid = (int)std::min<long long>(passes, (long long)lm->num_sms * 16);
     if (n_obs > 0) {
         int g1 = (int)std::min<long long>(((long long)lm->d.N + 255) / 256, (long long)lm->num_sms * 16);
         if (input_pntcld) k_alloc_observed<true><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
         else k_alloc_observed<false><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
         lm->launches++;
     }
-    if (vec == 4) {
-        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
-        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
+    if (vec == 8) {
+        if (input_pntcld) k_merge_ogm<true, 8><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
+        else k_merge_ogm<false, 8><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
+    } else if (vec == 4) {
+        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
+        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
     } else {
-        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
-        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs);
+        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
+        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
     }
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());

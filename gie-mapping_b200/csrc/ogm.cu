@@ -197,7 +197,64 @@ int launch_projective(gie_locmap *lm, const float *data, const SensorParam &sp, 
     return GIE_OK;
 }
 
+// ---- sensor pre-processing on the device (the MapMakers' host loops) -------------------------------------------------
+__device__ __forceinline__ float load_f32_unaligned(const unsigned char *p)
+{
+    uint32_t v = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    return __uint_as_float(v);
+}
+
+// Vlp16MapMaker::convertPyntCld (src/vlp16_map_maker.cpp:73-147): bin = (int)((atan2f(y, x) + (float)M_PI) / |theta_inc|),
+// ranges[ring][bin] = sqrtf(x*x + y*y), points visited in message order so the LAST point of a bin wins.  Here every point
+// does an atomicMax of (index + 1) << 32 | range bits; the largest index is the last point.
+__global__ void k_vlp16_bin(const unsigned char *__restrict__ data, int n, int step, int off_x, int off_y, int off_ring,
+                            int scan_num, int ring_num, float resolution, unsigned long long *__restrict__ img)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *p = data + (size_t)i * step;
+    float x = load_f32_unaligned(p + off_x), y = load_f32_unaligned(p + off_y);
+    int r = (int)p[off_ring] | ((int)p[off_ring + 1] << 8);
+    if (r >= ring_num) return;   // the reference would index past its scan lines here
+    int bin = (int)((atan2f(y, x) + 3.14159274f) / resolution);
+    if (bin >= 0 && bin < scan_num)
+        atomicMax(&img[(size_t)r * scan_num + bin], ((unsigned long long)(uint32_t)(i + 1) << 32) | __float_as_uint(sqrtf(x * x + y * y)));
+}
+__global__ void k_vlp16_finish(const unsigned long long *__restrict__ img, int n, float *__restrict__ ranges)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long v = img[i];
+    ranges[i] = v ? __uint_as_float((uint32_t)v) : INFINITY;   // scan lines start as INFINITY (:55-58)
+}
+// PntcldMapMaker::pntcld_process (src/pntcld_map_maker.cpp:49-61): the first cld_sz points' three consecutive floats at "x"
+__global__ void k_pc_repack(const unsigned char *__restrict__ data, int n, int step, int off_x, float *__restrict__ pts)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned char *p = data + (size_t)i * step + off_x;
+    pts[3 * i] = load_f32_unaligned(p); pts[3 * i + 1] = load_f32_unaligned(p + 4); pts[3 * i + 2] = load_f32_unaligned(p + 8);
+}
+
 }  // namespace
+
+int gie_launch_vlp16_bin(gie_locmap *lm, const unsigned char *raw_dev, int n, int step, int off_x, int off_y, int off_ring,
+                         int scan_num, int ring_num, float theta_inc, unsigned long long *img_dev, float *ranges_dev)
+{
+    const int cells = scan_num * ring_num;
+    GIE_CUDA_CHECK(cudaMemsetAsync(img_dev, 0, (size_t)cells * 8, lm->stream));
+    if (n > 0) k_vlp16_bin<<<(n + 255) / 256, 256, 0, lm->stream>>>(raw_dev, n, step, off_x, off_y, off_ring, scan_num, ring_num, fabsf(theta_inc), img_dev);
+    k_vlp16_finish<<<(cells + 255) / 256, 256, 0, lm->stream>>>(img_dev, cells, ranges_dev);
+    lm->launches += n > 0 ? 2 : 1;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+int gie_launch_pc_repack(gie_locmap *lm, const unsigned char *raw_dev, int n, int step, int off_x, float *pts_dev)
+{
+    if (n > 0) { k_pc_repack<<<(n + 255) / 256, 256, 0, lm->stream>>>(raw_dev, n, step, off_x, pts_dev); lm->launches++; }
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
 
 int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *, const float *pts_dev, int n, int fmp, int r2)
 {

@@ -67,6 +67,8 @@ struct WaveDev {
     uint32_t *snap_id;
     int display;   // display_glb_edt: record changed blocks for streaming
     int cluster_size, local_enter, local_spill;   // cluster-local mode of wave C
+    int epoch;   // value that marks a voxel as "already a wave-C seed" in m.wave_layer for THIS merge (never reused, so the
+                 // array needs no per-frame clearing; the reference rewrites _loc_wave_layer for every voxel)
 
     unsigned long long *trace;   // diagnostics (GIE_WAVE_TRACE=1): per wave-C level {n, t0, t_phase1, t_bar1, t_phase2, t_bar2} in ns
 };
@@ -164,19 +166,19 @@ __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev 
     const int nq = m.N / VEC;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
         const int id0 = q * VEC;
-        const int x0 = id0 % m.X, yz = id0 / m.X;
-        const int y = yz % m.Y, z = yz / m.Y;
-        int8_t types[VEC]; int wls[VEC];
+        int8_t types[VEC];
         if (VEC == 4) {
             char4 t4 = *reinterpret_cast<const char4 *>(m.glb_type + id0);
             types[0] = t4.x; types[1] = t4.y; types[2] = t4.z; types[3] = t4.w;
+            if ((t4.x | t4.y | t4.z | t4.w) == 0) continue;   // nothing known here (most of the volume)
         } else types[0] = m.glb_type[id0];
+        const int x0 = id0 % m.X, yz = id0 / m.X;
+        const int y = yz % m.Y, z = yz / m.Y;
 #pragma unroll
         for (int kk = 0; kk < VEC; kk++) {
             const int3 c = make_int3(x0 + kk, y, z);
             const int id = id0 + kk;
             const int8_t type = types[kk];
-            int wl = GIE_EMPTY_VALUE;
             if (type != GIE_VOX_UNKNOWN) {
                 unsigned long long pr = m.pair[id];
                 int3 cur_wr = gie_id2wr(gie_pair_id(pr));
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev 
                         }
                     }
                     if (lowered) {                                   // lower-in seed (frontier C)
-                        wl = 1;
+                        m.wave_layer[id] = w.epoch;
                         int i = atomicAdd(&w.cnt[C_C0], 1);
                         if (i < w.cap) { w.qC[0][i] = c_entry(c, C_ALWAYS); w.cseed_key[i] = new_key; }
                         else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
@@ -240,10 +242,7 @@ __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev 
                 }
             }
 
-            wls[kk] = wl;
         }
-        if (VEC == 4) *reinterpret_cast<int4 *>(m.wave_layer + id0) = make_int4(wls[0], wls[1], wls[2], wls[3]);
-        else m.wave_layer[id0] = wls[0];
     }
 }
 
@@ -438,16 +437,16 @@ __device__ void waveB_phase2(const LocDev &m, const HashDev &h, const WaveDev &w
             int col[6];
 #pragma unroll
             for (int d = 0; d < 6; d++) {   // colour swaps all in flight before any is looked at
-                col[d] = kind[d] == 1 ? gray : 1;
+                col[d] = kind[d] == 1 ? gray : w.epoch;
                 if (kind[d] == 1 && key[d] < old[d]) col[d] = atomicExch(&h.wave_layer[ni[d]], gray);
-                else if (kind[d] == 2) col[d] = atomicExch(&m.wave_layer[nid[d]], 1);
+                else if (kind[d] == 2) col[d] = atomicExch(&m.wave_layer[nid[d]], w.epoch);
             }
 #pragma unroll
             for (int d = 0; d < 6; d++) {
                 if (kind[d] == 1 && col[d] != gray) {
                     h.update_ct[ni[d]] = map_ct;
                     out_items[n_out++] = pack_glb(cg + DIRS6[d]);
-                } else if (kind[d] == 2 && col[d] != 1) in_items[n_in++] = c_entry(cg + DIRS6[d] - m.pvt, C_ALWAYS);
+                } else if (kind[d] == 2 && col[d] != w.epoch) in_items[n_in++] = c_entry(cg + DIRS6[d] - m.pvt, C_ALWAYS);
             }
         }
         q_push_warp(next, next_cnt, w.cap, out_items, n_out, h.status);
@@ -749,6 +748,7 @@ WaveDev make_wave_dev(gie_hashmap *hm)
     w.snap_id = hm->snap_id;
     w.trace = hm->wave_trace;
     w.cluster_size = hm->wave_cluster;
+    w.epoch = hm->merge_epoch;
     // enter the local mode when the frontier fits comfortably; leave it when the queues are more than half full
     w.local_enter = hm->wave_cluster * LQ_CAP / 4;
     w.local_spill = hm->wave_cluster * LQ_CAP / 2;
@@ -817,6 +817,7 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
 {
     gie_locmap *lm = hm->lm;
     const LocDev &m = lm->d;
+    hm->merge_epoch++;
     WaveDev w = make_wave_dev(hm);
     w.display = display;
     const int vec = (m.X % 4 == 0) ? 4 : 1;

@@ -64,6 +64,8 @@ def load_library():
         "gie_ogm_depth_dev": [p, p, p, i, i, f, f, f, f, i, i, i], "gie_ogm_depth_host": [p, p, p, i, i, f, f, f, f, i, i, i],
         "gie_hashmap_update_ogm": [p, i, i, i, i, p, p, p], "gie_edt_batch_update": [p], "gie_hashmap_merge_new_obsv": [p, i, i],
         "gie_hashmap_num_changed": [p, C.POINTER(i)], "gie_hashmap_stream_changed": [p, p, p, i, C.POINTER(i)],
+        "gie_ogm_vlp16_pointcloud2_host": [p, p, p, i, i, i, i, i, i, i, f, f, f, f, i, i],
+        "gie_vlp16_last_ranges": [p, i, i, i, i, p], "gie_ogm_pointcloud2_host": [p, p, p, i, i, i, i, i, i],
         "gie_make_projection": [p, p, p, p], "gie_locmap_set_projection": [p, p, p, p], "gie_locmap_calculate_pivots": [p, p],
         "gie_sync": [p], "gie_hashmap_num_blocks": [p, C.POINTER(i)], "gie_hashmap_export_blocks": [p, p, p, i],
         "gie_hashmap_wave_stats": [p, p], "gie_profile_enable": [p, i], "gie_profile_last": [p, p],
@@ -237,6 +239,26 @@ class GlbHashMap:
             rows, cols = a.shape
             _check(self.lib.gie_ogm_depth_host(lm._h, self._h, _hostptr(a), rows, cols, cx, cy, fx, fy, int(valid_nan),
                                                int(for_motion_planner), rbt_r2_grids))
+
+    def ogm_vlp16_pointcloud2(self, data, point_step, off_x, off_y, off_ring, scan_num, ring_num, theta_inc, theta_min, phi_inc,
+                              phi_min, for_motion_planner=False, rbt_r2_grids=0):
+        """Vlp16MapMaker::updateLocalOGM on raw PointCloud2 bytes (uint8 array of n * point_step)."""
+        a = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        n = a.size // point_step
+        _check(self.lib.gie_ogm_vlp16_pointcloud2_host(self._lMap._h, self._h, _hostptr(a), n, point_step, off_x, off_y, off_ring, scan_num,
+                                                       ring_num, theta_inc, theta_min, phi_inc, phi_min, int(for_motion_planner), rbt_r2_grids))
+        return n
+
+    def vlp16_last_ranges(self, n_points, point_step, scan_num, ring_num):
+        out = np.zeros((ring_num, scan_num), np.float32)
+        _check(self.lib.gie_vlp16_last_ranges(self._lMap._h, n_points, point_step, scan_num, ring_num, _hostptr(out)))
+        return out
+
+    def ogm_pointcloud2(self, data, point_step, off_x=0, max_points=0, for_motion_planner=False, rbt_r2_grids=0):
+        """PntcldMapMaker::updateLocalOGM on raw PointCloud2 bytes."""
+        a = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        _check(self.lib.gie_ogm_pointcloud2_host(self._lMap._h, self._h, _hostptr(a), a.size // point_step, point_step, off_x, max_points,
+                                                 int(for_motion_planner), rbt_r2_grids))
 
     # --- per-frame stages --------------------------------------------------------------------------------------
     def updateHashOGM(self, input_pynt, map_ct, stream_glb_ogm=False, ext_obsv=None):

@@ -191,3 +191,26 @@ def make_frames(cfg, n_frames, seed=42, start=None, dynamic=False):
                                      0.05, rs)
         frames.append(f)
     return frames
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Raw sensor_msgs/PointCloud2 payloads (what the reference's MapMakers receive before their host-side conversion)
+VLP16_POINT_DTYPE = np.dtype({"names": ["x", "y", "z", "intensity", "ring", "time"],
+                              "formats": ["<f4", "<f4", "<f4", "<f4", "<u2", "<f4"], "offsets": [0, 4, 8, 12, 16, 18], "itemsize": 22})
+
+
+def vlp16_pointcloud2(world, q, t, az=1800, rings=16, elev_min_deg=-15.0, elev_step_deg=2.0, max_range=100.0):
+    """velodyne_pointcloud layout (point_step 22: x, y, z, intensity f32, ring u16, time f32), azimuth-major firing order,
+    no-return rays dropped.  Returns (uint8 bytes, point_step, field offsets dict)."""
+    el = np.deg2rad(elev_min_deg + elev_step_deg * np.arange(rings))
+    azs = -np.pi + 2 * np.pi * (np.arange(az) + 0.37) / az
+    ce, se = np.cos(el)[None, :], np.sin(el)[None, :]
+    d_s = np.stack([ce * np.cos(azs)[:, None], ce * np.sin(azs)[:, None], np.broadcast_to(se, (az, rings))], axis=-1).reshape(-1, 3)
+    ring = np.broadcast_to(np.arange(rings)[None, :], (az, rings)).reshape(-1)
+    rng = world.cast(np.asarray(t, np.float64), d_s @ quat_to_rot(q).T)
+    ok = np.isfinite(rng) & (rng < max_range)
+    pts = np.zeros(int(ok.sum()), dtype=VLP16_POINT_DTYPE)
+    p = (d_s[ok] * rng[ok, None]).astype(np.float32)
+    pts["x"], pts["y"], pts["z"], pts["ring"] = p[:, 0], p[:, 1], p[:, 2], ring[ok]
+    pts["intensity"] = 1.0
+    return pts.view(np.uint8).reshape(-1).copy(), 22, dict(x=0, y=4, z=8, ring=16)

@@ -136,6 +136,22 @@ int gie_ogm_depth_dev(gie_locmap *lm, gie_hashmap *hm, const float *depth_dev, i
 int gie_ogm_depth_host(gie_locmap *lm, gie_hashmap *hm, const float *depth_host, int rows, int cols, float cx,
                        float cy, float fx, float fy, int valid_nan, int for_motion_planner, int rbt_r2_grids);
 
+/* Raw sensor_msgs/PointCloud2 front ends: the MapMakers' host-side conversion loops moved to the device (one upload of the
+ * message bytes, no per-ring copies).  data_host = msg->data, point_step = msg->point_step, off_* = field offsets.
+ *   Vlp16MapMaker::convertPyntCld + updateLocalOGM (src/vlp16_map_maker.cpp:52-147): float32 x,y and uint16 ring are binned
+ *     into the [ring_num][scan_num] horizontal-range image, bin = (int)((atan2f(y,x) + pi) / |theta_inc|), the last point of a
+ *     bin in message order wins, empty bins are INFINITY; then VLP_FAST::localOGMKernels.  (The reference calls glibc's atan2f
+ *     on the host; here it is CUDA's — a point within an ulp of a bin edge can land in the neighbouring bin.)
+ *   PntcldMapMaker::pntcld_process + updateLocalOGM (src/pntcld_map_maker.cpp:49-73): the three consecutive floats at off_x of
+ *     the first max_points points (cld_sz; 0 = no cap) become the float3 cloud; then PNTCLD_RAYCAST::localOGMKernels.
+ * gie_vlp16_last_ranges downloads the range image of the last vlp16_pointcloud2 call (same n_points / point_step). */
+int gie_ogm_vlp16_pointcloud2_host(gie_locmap *lm, gie_hashmap *hm, const void *data_host, int n_points, int point_step, int off_x,
+                                   int off_y, int off_ring, int scan_num, int ring_num, float theta_inc, float theta_min,
+                                   float phi_inc, float phi_min, int for_motion_planner, int rbt_r2_grids);
+int gie_vlp16_last_ranges(gie_locmap *lm, int n_points, int point_step, int scan_num, int ring_num, float *ranges_host);
+int gie_ogm_pointcloud2_host(gie_locmap *lm, gie_hashmap *hm, const void *data_host, int n_points, int point_step, int off_x,
+                             int max_points, int for_motion_planner, int rbt_r2_grids);
+
 /* GlbHashMap::updateHashOGM (glb_hash_map.cu:115-143) incl. allocHashTB (:58-113).
  *   stream_glb_ogm : record blocks whose voxel type changed, for gie_hashmap_stream_changed (unify_helper.cuh:103-113)
  *   n_obs, obs_*   : Ext_Obs_Wrapper's boxes (include/map_structure/pre_map.h:12-28), host arrays float[3*n_obs] lower-left /

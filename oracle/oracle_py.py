@@ -42,6 +42,7 @@ def lib():
         l.gor_batch_edt_bruteforce.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.gor_merge_new_obsv.argtypes = [C.c_void_p, C.c_int]
         l.gor_get_pivots.argtypes = [C.c_void_p, C.c_void_p]
+        l.gor_vlp16_bin.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_void_p]
         l.gor_set_ext_obs.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         l.gor_set_stream.argtypes = [C.c_void_p, C.c_int, C.c_int]
         l.gor_take_changed.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -168,6 +169,14 @@ class OracleMapper:
             p = vox["dist_id_pair"]
             vox["dist_id_pair"] = (p >> np.uint64(32)) | (p << np.uint64(32))
         return keys, vox
+
+
+def vlp16_bin(data, point_step, off_x, off_y, off_ring, scan_num, ring_num, theta_inc):
+    """Range image [ring_num, scan_num] from raw PointCloud2 bytes (Vlp16MapMaker::convertPyntCld)."""
+    a = np.ascontiguousarray(data, np.uint8).reshape(-1)
+    out = np.zeros((ring_num, scan_num), np.float32)
+    lib().gor_vlp16_bin(_p(a), a.size // point_step, point_step, off_x, off_y, off_ring, scan_num, ring_num, theta_inc, _p(out))
+    return out
 
 
 def batch_edt_bruteforce(glb_type):

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu.log 2>&1
+tail -12 gpurun_out/pytest_gpu.log
+timeout 300 python scratch/e2e_probe.py prof 2>&1 | cut -c1-150

@@ -134,3 +134,14 @@ def test_golden_box_hash_voxels(gie, oracle):
             assert v["vox_type"] == r["type"] and v["occ_val"] == r["occ"], (k, gcoord)
             assert v["dist_sq"] == r["dist"] and tuple(v["coc_glb"]) == tuple(r["coc"]), (k, gcoord)
     om.close()
+
+
+def test_vlp16_binning_restatement(gie, oracle):
+    """convertPyntCld restated: empty bins are INFINITY, the last point of a bin wins, ranges are horizontal."""
+    pts = np.zeros(4, dtype=gie.scenes.VLP16_POINT_DTYPE)
+    pts["x"], pts["y"], pts["ring"] = [1.0, 2.0, -3.0, 0.0], [0.0, 0.0, 0.0, 5.0], [3, 3, 0, 15]
+    img = oracle.vlp16_bin(pts.view(np.uint8), 22, 0, 4, 16, 440, 16, float(np.float32(2 * np.pi / 440)))
+    assert np.isinf(img).sum() == 440 * 16 - 2
+    assert img[3, 220] == 2.0            # atan2(0, +x) = 0 -> bin (0 + pi) / res = 220; the later point (range 2) wins
+    assert np.isinf(img[0]).all()        # atan2(0, -x) = pi -> bin 440 == scan_num: dropped, as in the reference (:137)
+    assert img[15, 330] == 5.0

@@ -298,3 +298,53 @@ def test_batch_edt_headline_size_vs_scipy(gie):
     sl = slice(None, None, 7)   # coc consistency on a strided subset (memory)
     zz, yy, xx = np.meshgrid(np.arange(Z)[sl], np.arange(Y)[sl], np.arange(X)[sl], indexing="ij")
     assert np.array_equal((xx - cx[sl, sl, sl]) ** 2 + (yy - cy[sl, sl, sl]) ** 2 + (zz - cz[sl, sl, sl]) ** 2, d[sl, sl, sl])
+
+
+def test_pointcloud2_front_ends(gie, oracle):
+    """the MapMakers' host loops on the device.  VLP-16: raw PointCloud2 bytes -> range image, bit-exact against
+    the oracle's restatement of convertPyntCld (incl. last-point-wins and an unaligned 22-byte point step), and the frame
+    integrated from it equals the frame integrated from the oracle's image.  Point cloud: strided xyz -> float3 with the cld_sz cap."""
+    cfg = gie.scenes.small_config("cfg2", (64, 64, 32), cutoff_grids_sq=49)
+    sp = cfg["scan_param"]
+    w = cfg["world"]
+    world = gie.scenes.World(w["extent"], w["height"], w["n_boxes"], seed=42, ceiling=w["ceiling"])
+    traj = gie.scenes.trajectory(3, start=cfg["start"], step=0.4)
+    mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+    try:
+        for k, (q, t) in enumerate(traj):
+            raw, step, off = gie.scenes.vlp16_pointcloud2(world, q, t)
+            ref_img = oracle.vlp16_bin(raw, step, off["x"], off["y"], off["ring"], sp["scan_num"], sp["ring_num"], sp["theta_inc"])
+            assert np.isfinite(ref_img).sum() > 1000
+            mp._time += 1
+            mp.loc_map.set_pose(q, t)
+            n = mp.hash_map.ogm_vlp16_pointcloud2(raw, step, off["x"], off["y"], off["ring"], sp["scan_num"], sp["ring_num"], sp["theta_inc"],
+                                                  sp["theta_min"], sp["phi_inc"], sp["phi_min"])
+            img = mp.hash_map.vlp16_last_ranges(n, step, sp["scan_num"], sp["ring_num"])
+            assert np.array_equal(img.view(np.uint32), ref_img.view(np.uint32)), f"frame {k}: range image differs in {(img != ref_img).sum()} bins"
+            mp.hash_map.updateHashOGM(False, mp._time)
+            mp.update_edt()
+            om.publishMap(dict(q=q, t=t, ranges=ref_img))
+            _cmp_frame(gie, mp, om, f"vlp16 pointcloud2 frame {k}")
+    finally:
+        mp.close()
+        om.close()
+    # generic point cloud: 32-byte stride, xyz at offset 4, capped at cld_sz
+    cfg = gie.scenes.small_config("cfg4", (48, 48, 24), cutoff_grids_sq=64)
+    frames = gie.scenes.make_frames(cfg, 2)
+    mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+    try:
+        for k, f in enumerate(frames):
+            pts = f["points"]
+            cap = pts.shape[0] - 100
+            raw = np.zeros((pts.shape[0], 32), np.uint8)
+            raw[:, 4:16] = pts.view(np.uint8).reshape(-1, 12)
+            mp._time += 1
+            mp.loc_map.set_pose(f["q"], f["t"])
+            mp.hash_map.ogm_pointcloud2(raw, 32, off_x=4, max_points=cap)
+            mp.hash_map.updateHashOGM(True, mp._time)
+            mp.update_edt()
+            om.publishMap(dict(q=f["q"], t=f["t"], points=pts[:cap]))
+            _cmp_frame(gie, mp, om, f"pointcloud2 frame {k}")
+    finally:
+        mp.close()
+        om.close()
