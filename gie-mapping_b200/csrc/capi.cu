@@ -67,6 +67,9 @@ ArrInfo arr_info(gie_locmap *lm, int which)
         case GIE_ARR_AUX: return { m.aux, n * 4 };
         case GIE_ARR_COC_AUX: return { m.coc_aux, n * 4 };
         case GIE_ARR_PAIR: return { m.pair, n * 8 };
+        case GIE_ARR_EDT_G2: return { lm->g2, n * 4 };
+        case GIE_ARR_EDT_CXY: return { lm->cxy, n * 4 };
+        case GIE_ARR_EDT_NCOLS: return { lm->edt_meta, (size_t)m.Z * 4 };
         default: return { nullptr, 0 };
     }
 }
@@ -493,6 +496,16 @@ int gie_edt_batch_update(gie_locmap *lm)
 {
     if (!lm) return GIE_ERR_INVALID_ARG;
     return gie_launch_batch_edt(lm);
+}
+int gie_edt_xy_sweeps(gie_locmap *lm)
+{
+    if (!lm) return GIE_ERR_INVALID_ARG;
+    return gie_launch_edt_xy(lm);
+}
+int gie_edt_z_sweep(gie_locmap *lm, int max_width_override)
+{
+    if (!lm || max_width_override < 0) return GIE_ERR_INVALID_ARG;
+    return gie_launch_edt_z(lm, max_width_override);
 }
 int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt)
 {

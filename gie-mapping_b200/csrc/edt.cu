@@ -338,6 +338,39 @@ int gie_edt_prepare(gie_locmap *lm)
     return GIE_OK;
 }
 
+// The two halves of the batch EDT as separate launches, for the multi-GPU path (gie-mapping_b200/sharded.py): the y and x
+// sweeps are local to a z-slab of the volume, the z sweep needs whole z columns and runs after the slabs were re-partitioned.
+int gie_launch_edt_xy(gie_locmap *lm)
+{
+    const LocDev &m = lm->d;
+    const int WY = (m.Y + 31) / 32;
+    const int L = m.X > m.Z ? m.X : m.Z;
+    int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
+    GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
+    k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
+    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                                      lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
+    lm->launches += 3;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
+{
+    LocDev m = lm->d;
+    if (max_width_override > 0) m.max_width = max_width_override;
+    const int XG = (m.X + 31) / 32;
+    const int L = m.X > m.Z ? m.X : m.Z;
+    int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
+    GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
+    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
+                                                                      lm->work_counters + 1, m.Y * XG, XG);
+    lm->launches += 2;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
 int gie_launch_batch_edt(gie_locmap *lm)
 {
     const LocDev &m = lm->d;

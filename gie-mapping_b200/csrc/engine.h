@@ -100,6 +100,8 @@ int gie_launch_gather_changed(gie_hashmap *hm, int first, int n, int32_t *keys_d
 // edt.cu
 int gie_edt_prepare(gie_locmap *lm);
 int gie_launch_batch_edt(gie_locmap *lm);
+int gie_launch_edt_xy(gie_locmap *lm);
+int gie_launch_edt_z(gie_locmap *lm, int max_width_override);
 // wave.cu
 int gie_wave_prepare(gie_hashmap *hm);
 int gie_launch_merge(gie_hashmap *hm, int map_ct, int display_glb_edt);

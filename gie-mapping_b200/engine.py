@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 ARR_RAY_COUNT, ARR_INST_TYPE, ARR_GLB_TYPE, ARR_EDT, ARR_AUX, ARR_COC_AUX, ARR_PAIR = range(7)
+ARR_EDT_G2, ARR_EDT_CXY, ARR_EDT_NCOLS = 7, 8, 9
 _ARR_DTYPE = {ARR_RAY_COUNT: np.int32, ARR_INST_TYPE: np.int8, ARR_GLB_TYPE: np.int8, ARR_EDT: np.float32,
               ARR_AUX: np.int32, ARR_COC_AUX: np.int32, ARR_PAIR: np.uint64}
 STAGE_NAMES = ["ogm", "hash_merge", "edt_pack", "edt_x", "edt_z", "mark_frontier", "waves", "commit"]
@@ -66,6 +67,7 @@ def load_library():
         "gie_hashmap_num_changed": [p, C.POINTER(i)], "gie_hashmap_stream_changed": [p, p, p, i, C.POINTER(i)],
         "gie_ogm_vlp16_pointcloud2_host": [p, p, p, i, i, i, i, i, i, i, f, f, f, f, i, i],
         "gie_vlp16_last_ranges": [p, i, i, i, i, p], "gie_ogm_pointcloud2_host": [p, p, p, i, i, i, i, i, i],
+        "gie_edt_xy_sweeps": [p], "gie_edt_z_sweep": [p, i],
         "gie_make_projection": [p, p, p, p], "gie_locmap_set_projection": [p, p, p, p], "gie_locmap_calculate_pivots": [p, p],
         "gie_sync": [p], "gie_hashmap_num_blocks": [p, C.POINTER(i)], "gie_hashmap_export_blocks": [p, p, p, i],
         "gie_hashmap_wave_stats": [p, p], "gie_profile_enable": [p, i], "gie_profile_last": [p, p],
@@ -159,6 +161,12 @@ class LocMap:
     def batchEDTUpdate(self):
         """EDT_OCC::batchEDTUpdate (src/kernel/edt/local_edt.cu:7-28)."""
         _check(self.lib.gie_edt_batch_update(self._h))
+
+    def edt_xy_sweeps(self):
+        _check(self.lib.gie_edt_xy_sweeps(self._h))
+
+    def edt_z_sweep(self, max_width_override=0):
+        _check(self.lib.gie_edt_z_sweep(self._h, int(max_width_override)))
 
     def profile_enable(self, on=True):
         _check(self.lib.gie_profile_enable(self._h, int(on)))

@@ -98,7 +98,11 @@ int gie_locmap_copy_edt_to_host(gie_locmap *lm, float *edt_host);
 int gie_locmap_convert_costmap(gie_locmap *lm, gie_seendist *seendist_host);
 /* raw device views for GPU consumers (LocMap::_glb_type, _edt_D, _aux, _coc_idx_aux, _dist_id_pair; local_batch.h:540-562) */
 enum gie_array { GIE_ARR_RAY_COUNT = 0, GIE_ARR_INST_TYPE = 1, GIE_ARR_GLB_TYPE = 2, GIE_ARR_EDT = 3, GIE_ARR_AUX = 4,
-                 GIE_ARR_COC_AUX = 5, GIE_ARR_PAIR = 6 };
+                 GIE_ARR_COC_AUX = 5, GIE_ARR_PAIR = 6,
+                 /* batch-EDT intermediates, for the multi-GPU re-partition (gie_edt_xy_sweeps / gie_edt_z_sweep) */
+                 GIE_ARR_EDT_G2 = 7,    /* int32 [Z][Y][X]: in-slice squared distance after the y and x sweeps */
+                 GIE_ARR_EDT_CXY = 8,   /* int32 [Z][Y][X]: closest obstacle of the slice, x | y << 16 */
+                 GIE_ARR_EDT_NCOLS = 9  /* int32 [Z]: obstacle-bearing columns per slice (0 = the slice is skipped) */ };
 int gie_locmap_device_ptr(gie_locmap *lm, int which, void **dev_ptr, size_t *bytes);
 int gie_locmap_download(gie_locmap *lm, int which, void *host_out);
 /* test hook: overwrite _glb_type (N bytes) so the batch EDT can be driven directly */
@@ -162,6 +166,14 @@ int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int st
                            const float *obs_ll_host, const float *obs_ur_host, const unsigned char *obs_activated_host);
 /* EDT_OCC::batchEDTUpdate (src/kernel/edt/local_edt.cu:7-28); cuTT plans are not needed */
 int gie_edt_batch_update(gie_locmap *lm);
+/* The two halves of gie_edt_batch_update as separate calls, for volumes sharded across GPUs (no reference counterpart: the
+ * reference is single-GPU).  gie_edt_xy_sweeps runs EDTphase1+2 on this map's slices (local to a z-slab) and leaves
+ * GIE_ARR_EDT_G2 / _CXY / _NCOLS; gie_edt_z_sweep runs EDTphase3 over whatever those three arrays hold — after the caller
+ * re-partitioned them from z-slabs to y-slabs (gie-mapping_b200/sharded.py does it with NCCL all-to-all) — and writes
+ * GIE_ARR_AUX / GIE_ARR_COC_AUX.  max_width_override = X+Y+Z of the WHOLE volume (the "sees nothing" sentinel,
+ * local_batch.h:44), 0 = this map's own. */
+int gie_edt_xy_sweeps(gie_locmap *lm);
+int gie_edt_z_sweep(gie_locmap *lm, int max_width_override);
 /* GlbHashMap::mergeNewObsv (glb_hash_map.cu:146-207).  display_glb_edt: record blocks whose distances changed
  * (wave_core.cuh:128-134,250-256; unify_helper.cuh:510-520) for gie_hashmap_stream_changed. */
 int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt);
