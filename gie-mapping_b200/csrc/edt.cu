@@ -32,6 +32,26 @@ constexpr int RING = 16;      // stack entries per lane kept in shared memory
 constexpr int XS_SMEM_INTS_PER_WARP = 2 * 32 * 17 + 2 * RING * 32;
 constexpr int XS_SMEM_BYTES = WARPS_PER_CTA * XS_SMEM_INTS_PER_WARP * 4;
 
+// y pass, step 1: OCCUPIED bits of 32 consecutive y per (z, wy, x) -> low word of ytab.  One thread per word, x fastest:
+// 4 M independent threads at 512^3, each with 32 coalesced byte loads in flight.
+__global__ void __launch_bounds__(128) k_edt_ybits(LocDev m, unsigned long long *__restrict__ ytab, int WY)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, wy = blockIdx.y, z = blockIdx.z;
+    if (x >= m.X) return;
+    const int ybase = wy * 32, n = min(32, m.Y - ybase);
+    const int8_t *col = m.glb_type + ((size_t)z * m.Y + ybase) * m.X + x;
+    uint32_t w = 0;
+    if (n == 32) {
+#pragma unroll
+        for (int b = 0; b < 32; b++) w |= (uint32_t)(col[(size_t)b * m.X] == GIE_VOX_OCCUPIED) << b;
+    } else {
+        for (int b = 0; b < n; b++) w |= (uint32_t)(col[(size_t)b * m.X] == GIE_VOX_OCCUPIED) << b;
+    }
+    ytab[((size_t)z * WY + wy) * m.X + x] = w;
+}
+
+// y pass, step 2: per column (z, x) link every word to the nearest set bit below / above it, and compact the columns of the
+// slice that hold an obstacle.  One CTA per slice, one thread per column; touches only ytab (0.25 B/voxel).
 __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long *__restrict__ ytab, int WY,
                                                     int *__restrict__ col_list, int *__restrict__ n_cols)
 {
@@ -40,20 +60,17 @@ __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long
     const int lane = x & 31, wid = x >> 5;
     bool any = false;
     if (x < m.X) {
-        const int8_t *col = m.glb_type + (size_t)z * m.X * m.Y + x;
         unsigned long long *out = ytab + (size_t)z * WY * m.X + x;
-        int lo_prev = 0xffff;
-        for (int wy = 0; wy < WY; wy++) {
-            uint32_t w = 0;
-            int ybase = wy * 32;
-            int n = min(32, m.Y - ybase);
-#pragma unroll 8
-            for (int b = 0; b < n; b++)
-                w |= (uint32_t)(col[(size_t)(ybase + b) * m.X] == GIE_VOX_OCCUPIED) << b;
-            out[(size_t)wy * m.X] = (unsigned long long)w | ((unsigned long long)lo_prev << 32);
-            if (w) { lo_prev = ybase + 31 - __clz(w); any = true; }
-        }
+        uint32_t any_bits = 0;
+        for (int wy = 0; wy < WY; wy++) any_bits |= (uint32_t)out[(size_t)wy * m.X];
+        any = any_bits != 0;
         if (any) {   // a column without obstacles is never visited by the x sweep
+            int lo_prev = 0xffff;
+            for (int wy = 0; wy < WY; wy++) {
+                uint32_t w = (uint32_t)out[(size_t)wy * m.X];
+                out[(size_t)wy * m.X] = (unsigned long long)w | ((unsigned long long)lo_prev << 32);
+                if (w) lo_prev = wy * 32 + 31 - __clz(w);
+            }
             int hi_next = 0xffff;
             for (int wy = WY - 1; wy >= 0; wy--) {
                 unsigned long long e = out[(size_t)wy * m.X];
@@ -347,11 +364,12 @@ int gie_launch_edt_xy(gie_locmap *lm)
     const int L = m.X > m.Z ? m.X : m.Z;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
+    k_edt_ybits<<<dim3((m.X + 127) / 128, WY, m.Z), 128, 0, lm->stream>>>(m, lm->ytab, WY);
     k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
     k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
                                                                       lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
-    lm->launches += 3;
+    lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
@@ -380,6 +398,7 @@ int gie_launch_batch_edt(gie_locmap *lm)
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     {
         StageTimer t(lm, GIE_ST_EDT_PACK);
+        k_edt_ybits<<<dim3((m.X + 127) / 128, WY, m.Z), 128, 0, lm->stream>>>(m, lm->ytab, WY);
         k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
         k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
     }
@@ -395,7 +414,7 @@ int gie_launch_batch_edt(gie_locmap *lm)
                                                                           (uint2 *)lm->stack_scratch, L, lm->work_counters + 1,
                                                                           m.Y * XG, XG);
     }
-    lm->launches += 4;
+    lm->launches += 5;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

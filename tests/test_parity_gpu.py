@@ -348,3 +348,49 @@ def test_pointcloud2_front_ends(gie, oracle):
     finally:
         mp.close()
         om.close()
+
+
+def _golden_cases():
+    import glob
+    import os
+    return sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _golden_cases(), ids=lambda p: p.split("/")[-1][:-4])
+def test_cuda_engine_vs_reference_golden(gie, path):
+    """The CUDA engine directly against the fixtures produced by the reference's OWN CUDA sources on a B200
+    (tests/golden/*.npz, oracle/gen_golden.py): bit-exact occupancy, batch dist_sq and committed (dist, coc) on every frame
+    before the first wavefront activity; afterwards the reference is schedule dependent, so >= 95 % identical
+    voxels with the differing ones in the majority closer here — the same bar the oracle is held to."""
+    g = np.load(path)
+    cfg = gie.scenes.small_config(str(g["cfg_name"]), tuple(int(v) for v in g["size"]), cutoff_grids_sq=int(g["cutoff"]))
+    frames = gie.scenes.make_frames(cfg, int(g["nframes"]), dynamic=bool(g["dynamic"]))
+    mp = gie.Mapper(cfg)
+    waves_seen, exact_frames = False, 0
+    try:
+        for k, f in enumerate(frames):
+            mp.publishMap(f)
+            mp.hash_map.sync()
+            st = mp.hash_map.wave_stats()
+            t = mp.loc_map.download(gie.ARR_GLB_TYPE)
+            pair = mp.loc_map.download(gie.ARR_PAIR)
+            aux = mp.loc_map.download(gie.ARR_AUX)
+            rt = g[f"f{k}_glb_type"]
+            known = (rt != 0) & (t != 0)
+            od, oid = (pair >> np.uint64(32)).astype(np.int64), (pair & np.uint64(0xffffffff)).astype(np.int64)
+            rd, rid = g[f"f{k}_pair_dist"].astype(np.int64), g[f"f{k}_pair_id"].astype(np.int64) & 0xffffffff
+            assert ((t != 0) != (rt != 0)).sum() == 0, f"frame {k}: known/unknown set differs"
+            if not waves_seen and (st["fA"] + st["fB"] + st["fC"]) == 0:
+                assert np.array_equal(t, rt), f"frame {k}: glb_type"
+                assert np.array_equal(aux[known], g[f"f{k}_aux"][known]), f"frame {k}: batch dist_sq"
+                assert np.array_equal(od[known], rd[known]) and np.array_equal(oid[known], rid[known]), f"frame {k}: pair"
+                exact_frames += 1
+            else:
+                waves_seen = True
+                assert (t != rt).sum() <= 8, f"frame {k}: glb_type differs in {(t != rt).sum()} voxels"
+                assert (od[known] == rd[known]).mean() >= 0.95, f"frame {k}"
+                diff = (od - rd)[known & (od < 900000) & (rd < 900000)]
+                assert (diff < 0).sum() >= (diff > 0).sum(), f"frame {k}: reference closer more often"
+        assert exact_frames >= 1
+    finally:
+        mp.close()
