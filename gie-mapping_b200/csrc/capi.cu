@@ -330,7 +330,7 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
     cudaFree(hm->cseed_key); cudaFree(hm->counters); cudaFree(hm->barrier); cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
-    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace);
+    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list); cudaFree(hm->blk_count);
     cudaFreeHost(hm->status_host); cudaFreeHost(hm->stats_host);
     if (hm->lm->hm == hm) hm->lm->hm = nullptr;
     delete hm;

@@ -16,6 +16,7 @@
 // identically by the CPU oracle.
 #include "engine.h"
 #include <cooperative_groups.h>
+#include <algorithm>
 
 namespace {
 
@@ -158,102 +159,114 @@ __global__ void __launch_bounds__(256) k_mark(LocDev m, HashDev h)
     }
 }
 
-// obtainFrontiers (unify_helper.cuh:275-446).  pair[] is read-only here: a lowered own pair (frontier C seed) is
-// deferred into cseed_key and applied by the wave kernel, which removes the reference's _g/_coc_idx backup arrays.
-// CH = 4: a thread first looks at 16 voxel types with one 16-byte load and skips the lot when nothing is known there (most of
-// the volume), which keeps enough bytes in flight per thread to stream glb_type at DRAM speed.
-template <int VEC, int CH>
-__global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct)
+// The per-voxel kernels of the merge (frontiers, commit) walk the ALLOCATED blocks that intersect the local volume instead
+// of the whole volume: a known voxel always has a block, and in the headline scene the allocated blocks cover ~5 % of the
+// 512^3 volume.  k_list_blocks compacts the dense block table into that list once per merge; the kernels then take one
+// block per CTA pass (hash pools are then read as 512 consecutive entries per field).
+__global__ void __launch_bounds__(256) k_list_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int *__restrict__ count)
 {
-    const int nsg = m.N / (VEC * CH);
-    for (int sg = blockIdx.x * blockDim.x + threadIdx.x; sg < nsg; sg += gridDim.x * blockDim.x) {
-      int tw[CH];
-      if (CH == 4) {
-          int4 t16 = *reinterpret_cast<const int4 *>(m.glb_type + (size_t)sg * VEC * CH);
-          if ((t16.x | t16.y | t16.z | t16.w) == 0) continue;
-          tw[0] = t16.x; tw[1] = t16.y; tw[2] = t16.z; tw[3] = t16.w;
-      }
+    const int lane = threadIdx.x & 31;
+    const int padded = (entries + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
+        bool take = false;
+        if (i < entries && __ldcg(&h.btab[i]) >= 0) {
+            int3 k = make_int3(i % h.tab_dim.x, (i / h.tab_dim.x) % h.tab_dim.y, i / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
+            int3 lo = make_int3(k.x * 8, k.y * 8, k.z * 8) - m.pvt;   // local coords of the block's first voxel
+            take = lo.x + 7 >= 0 && lo.x < m.X && lo.y + 7 >= 0 && lo.y < m.Y && lo.z + 7 >= 0 && lo.z < m.Z;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, take);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(count, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) list[base + __popc(bal & ((1u << lane) - 1))] = i;
+    }
+}
+// local coordinate of voxel v (engine order, x fastest) of the block at table index ti; false when outside the volume
+__device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev &h, int ti, int v, int3 &c)
+{
+    int3 k = make_int3(ti % h.tab_dim.x, (ti / h.tab_dim.x) % h.tab_dim.y, ti / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
+    c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - m.pvt;
+    return gie_inside_loc(m, c);
+}
+
+// obtainFrontiers (unify_helper.cuh:275-446) for one known voxel.  pair[] is read-only here: a lowered own pair (frontier C
+// seed) is deferred into cseed_key and applied by the wave kernel, which removes the reference's _g/_coc_idx backup arrays.
+__device__ __forceinline__ void frontier_voxel(const LocDev &m, const HashDev &h, const WaveDev &w, int map_ct, int3 c, int id, int8_t type)
+{
+    unsigned long long pr = m.pair[id];
+    int3 cur_wr = gie_id2wr(gie_pair_id(pr));
+    int3 cur_coc_glb = cur_wr + m.upvt;
+    int3 cur_coc_buf = cur_coc_glb - m.pvt;
+    int cur_dist = gie_pair_dist(pr);
+    if (gie_inside_loc(m, cur_coc_buf)) {
+        bool nbr_unknown = false, lowered = false;
+        unsigned long long new_key = 0;
 #pragma unroll
-      for (int gq = 0; gq < CH; gq++) {
-        const int id0 = (sg * CH + gq) * VEC;
-        int8_t types[VEC];
-        if (VEC == 4) {
-            int t4 = CH == 4 ? tw[gq] : *reinterpret_cast<const int *>(m.glb_type + id0);
-            if (t4 == 0) continue;   // nothing known here
-            types[0] = (int8_t)t4; types[1] = (int8_t)(t4 >> 8); types[2] = (int8_t)(t4 >> 16); types[3] = (int8_t)(t4 >> 24);
-        } else types[0] = m.glb_type[id0];
-        const int x0 = id0 % m.X, yz = id0 / m.X;
-        const int y = yz % m.Y, z = yz / m.Y;
-#pragma unroll
-        for (int kk = 0; kk < VEC; kk++) {
-            const int3 c = make_int3(x0 + kk, y, z);
-            const int id = id0 + kk;
-            const int8_t type = types[kk];
-            if (type != GIE_VOX_UNKNOWN) {
-                unsigned long long pr = m.pair[id];
-                int3 cur_wr = gie_id2wr(gie_pair_id(pr));
-                int3 cur_coc_glb = cur_wr + m.upvt;
-                int3 cur_coc_buf = cur_coc_glb - m.pvt;
-                int cur_dist = gie_pair_dist(pr);
-                if (gie_inside_loc(m, cur_coc_buf)) {
-                    bool nbr_unknown = false, lowered = false;
-                    unsigned long long new_key = 0;
-    #pragma unroll
-                    for (int d = 0; d < 6; d++) {
-                        int3 nb = c + DIRS6[d];
-                        if (gie_inside_loc(m, nb)) {
-                            int nid = gie_lidx(m, nb);
-                            if (m.glb_type[nid] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
-                            int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
-                            int3 ncb = nwr + m.upvt - m.pvt;
-                            if (!gie_inside_loc(m, ncb) && gie_inside_wr(nwr)) {
-                                int d2 = sqd3(ncb, c);
-                                if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
-                            }
-                        } else {
-                            int3 nglb = nb + m.pvt;
-                            size_t vi;
-                            if (!vox_ref(h, nglb, vi)) { nbr_unknown = true; continue; }
-                            if (h.vox_type[vi] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
-                            int ndist = h.dist_sq[vi];
-                            if (gie_invalid_dist_glb(ndist)) continue;
-                            int3 ncoc = gie_unpack_coc(h.coc_glb[vi]);
-                            if (gie_invalid_coc_glb(ncoc)) continue;
-                            int3 nwr = ncoc - m.upvt;
-                            bool n_valid = gie_inside_wr(nwr);
-                            int3 ncb = ncoc - m.pvt;
-                            bool n_local = gie_inside_loc(m, ncb);
-                            if (!n_local && n_valid) {
-                                int d2 = sqd3(ncb, c);
-                                if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
-                            }
-                            if (m.fast) continue;
-                            int c2n = sqd3(nb, cur_coc_buf);
-                            if (c2n < ndist) {                       // lower-out seed (frontier B)
-                                h.wave_layer[vi] = 1; h.update_ct[vi] = map_ct;
-                                h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
-                                q_push(w.qB[0], &w.cnt[C_B0], w.cap, pack_glb(nglb), h.status);
-                            } else if (c2n > ndist && n_local) {     // raise-out seed (frontier A)
-                                if (m.glb_type[gie_lidx(m, ncb)] != GIE_VOX_OCCUPIED) {
-                                    h.dist_sq[vi] = c2n; h.coc_glb[vi] = gie_pack_coc(cur_coc_glb); h.wave_layer[vi] = -map_ct;
-                                    h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
-                                    q_push(w.qA[0], &w.cnt[C_A0], w.cap, pack_glb(nglb), h.status);
-                                }
-                            }
-                        }
+        for (int d = 0; d < 6; d++) {
+            int3 nb = c + DIRS6[d];
+            if (gie_inside_loc(m, nb)) {
+                int nid = gie_lidx(m, nb);
+                if (m.glb_type[nid] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
+                int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
+                int3 ncb = nwr + m.upvt - m.pvt;
+                if (!gie_inside_loc(m, ncb) && gie_inside_wr(nwr)) {
+                    int d2 = sqd3(ncb, c);
+                    if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
+                }
+            } else {
+                int3 nglb = nb + m.pvt;
+                size_t vi;
+                if (!vox_ref(h, nglb, vi)) { nbr_unknown = true; continue; }
+                if (h.vox_type[vi] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
+                int ndist = h.dist_sq[vi];
+                if (gie_invalid_dist_glb(ndist)) continue;
+                int3 ncoc = gie_unpack_coc(h.coc_glb[vi]);
+                if (gie_invalid_coc_glb(ncoc)) continue;
+                int3 nwr = ncoc - m.upvt;
+                bool n_valid = gie_inside_wr(nwr);
+                int3 ncb = ncoc - m.pvt;
+                bool n_local = gie_inside_loc(m, ncb);
+                if (!n_local && n_valid) {
+                    int d2 = sqd3(ncb, c);
+                    if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
+                }
+                if (m.fast) continue;
+                int c2n = sqd3(nb, cur_coc_buf);
+                if (c2n < ndist) {                       // lower-out seed (frontier B)
+                    h.wave_layer[vi] = 1; h.update_ct[vi] = map_ct;
+                    h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
+                    q_push(w.qB[0], &w.cnt[C_B0], w.cap, pack_glb(nglb), h.status);
+                } else if (c2n > ndist && n_local) {     // raise-out seed (frontier A)
+                    if (m.glb_type[gie_lidx(m, ncb)] != GIE_VOX_OCCUPIED) {
+                        h.dist_sq[vi] = c2n; h.coc_glb[vi] = gie_pack_coc(cur_coc_glb); h.wave_layer[vi] = -map_ct;
+                        h.pair[vi] = gie_mk_pair(c2n, gie_wr2id(cur_wr));
+                        q_push(w.qA[0], &w.cnt[C_A0], w.cap, pack_glb(nglb), h.status);
                     }
-                    if (lowered) {                                   // lower-in seed (frontier C)
-                        m.wave_layer[id] = w.epoch;
-                        int i = atomicAdd(&w.cnt[C_C0], 1);
-                        if (i < w.cap) { w.qC[0][i] = c_entry(c, C_ALWAYS); w.cseed_key[i] = new_key; }
-                        else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
-                    }
-                    if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
                 }
             }
-
         }
-      }
+        if (lowered) {                                   // lower-in seed (frontier C)
+            m.wave_layer[id] = w.epoch;
+            int i = atomicAdd(&w.cnt[C_C0], 1);
+            if (i < w.cap) { w.qC[0][i] = c_entry(c, C_ALWAYS); w.cseed_key[i] = new_key; }
+            else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);
+        }
+        if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
+    }
+}
+__global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct, const int *__restrict__ list,
+                                                   const int *__restrict__ count)
+{
+    const int n = __ldcg(count);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int ti = __ldcg(&list[b]);
+        for (int v = threadIdx.x; v < 512; v += blockDim.x) {
+            int3 c;
+            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            const int id = gie_lidx(m, c);
+            const int8_t type = m.glb_type[id];
+            if (type != GIE_VOX_UNKNOWN) frontier_voxel(m, h, w, map_ct, c, id, type);
+        }
     }
 }
 
@@ -703,34 +716,19 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) k_waves(LocDev m, HashDev h, 
     }
 }
 
-// UpdateHashBatch (unify_helper.cuh:448-523)
-template <int VEC, int CH>
-__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display)
+// UpdateHashBatch (unify_helper.cuh:448-523), one allocated block per CTA pass (see k_list_blocks)
+__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int *__restrict__ list, const int *__restrict__ count)
 {
-    const int nsg = m.N / (VEC * CH);
-    for (int sg = blockIdx.x * blockDim.x + threadIdx.x; sg < nsg; sg += gridDim.x * blockDim.x) {
-      int tw[CH];
-      if (CH == 4) {   // 16 types at once, see k_frontiers
-          int4 t16 = *reinterpret_cast<const int4 *>(m.glb_type + (size_t)sg * VEC * CH);
-          if ((t16.x | t16.y | t16.z | t16.w) == 0) continue;
-          tw[0] = t16.x; tw[1] = t16.y; tw[2] = t16.z; tw[3] = t16.w;
-      }
-#pragma unroll
-      for (int gq = 0; gq < CH; gq++) {
-        const int id0 = (sg * CH + gq) * VEC;
-        int8_t types[VEC];
-        if (VEC == 4) {
-            int t4 = CH == 4 ? tw[gq] : *reinterpret_cast<const int *>(m.glb_type + id0);
-            if (t4 == 0) continue;
-            types[0] = (int8_t)t4; types[1] = (int8_t)(t4 >> 8); types[2] = (int8_t)(t4 >> 16); types[3] = (int8_t)(t4 >> 24);
-        } else types[0] = m.glb_type[id0];
-        const int x0 = id0 % m.X, yz = id0 / m.X;
-        const int y = yz % m.Y, z = yz / m.Y;
-#pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            const int8_t type = types[k];
+    const int n = __ldcg(count);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int ti = __ldcg(&list[b]);
+        const int blk = __ldcg(&h.btab[ti]);
+        for (int v = threadIdx.x; v < 512; v += blockDim.x) {
+            int3 c;
+            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            const int id = gie_lidx(m, c);
+            const int8_t type = m.glb_type[id];
             if (type == GIE_VOX_UNKNOWN) continue;
-            const int id = id0 + k;
             unsigned long long pr = m.pair[id];
             int dist = gie_pair_dist(pr);
             uint32_t pid = gie_pair_id(pr);
@@ -738,10 +736,7 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display
                 if (pid == 0xffffffffu) m.edt[id] = (float)m.max_loc_dist_sq;
                 continue;
             }
-            int3 glb = make_int3(x0 + k, y, z) + m.pvt;
-            int blk = gie_block_of(h, glb);
-            if (blk < 0) continue;
-            size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
+            size_t vi = (size_t)blk * 512 + v;
             h.coc_glb[vi] = gie_pack_coc(gie_id2wr(pid) + m.upvt);
             if (display && h.dist_sq[vi] != dist) h.dirty[blk] = 1;   // unify_helper.cuh:510-520
             h.dist_sq[vi] = dist;
@@ -749,7 +744,6 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display
             h.pair[vi] = pr;
             if (type == GIE_VOX_FNT) h.vox_type[vi] = GIE_VOX_FNT;
         }
-      }
     }
 }
 
@@ -826,6 +820,8 @@ int gie_wave_prepare(gie_hashmap *hm)
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_pair, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_flags, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->snap_id, cap * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->blk_list, hm->tab_entries * sizeof(int)));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->blk_count, sizeof(int)));
     if (getenv("GIE_WAVE_TRACE")) {
         GIE_CUDA_CHECK(cudaMalloc(&hm->wave_trace, (size_t)TRACE_LEVELS * 10 * 8));
         GIE_CUDA_CHECK(cudaMemset(hm->wave_trace, 0, (size_t)TRACE_LEVELS * 10 * 8));
@@ -848,15 +844,12 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->counters, 0, C_COUNT * sizeof(int), lm->stream));
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, (size_t)(hm->wave_ctas + 1) * 32 * sizeof(unsigned int), lm->stream));
-        if (vec == 4) {
-            k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
-            // CH = 1 here: known voxels come in clusters and each costs a 6-neighbour gather, so 16 voxels per thread
-            // serialises the work of the few busy threads (measured 0.60 -> 0.69 ms)
-            k_frontiers<4, 1><<<grid, 256, 0, lm->stream>>>(m, hm->d, w, map_ct);
-        } else {
-            k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
-            k_frontiers<1, 1><<<grid, 256, 0, lm->stream>>>(m, hm->d, w, map_ct);
-        }
+        GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
+        const int entries = (int)hm->tab_entries;
+        k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(m, hm->d, entries, hm->blk_list, hm->blk_count);
+        if (vec == 4) k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+        else k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+        k_frontiers<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
     }
     {
         StageTimer t(lm, GIE_ST_WAVES);
@@ -884,12 +877,10 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        if (vec == 4 && m.X % 16 == 0) k_commit<4, 4><<<grid, 256, 0, lm->stream>>>(m, hm->d, display);
-        else if (vec == 4) k_commit<4, 1><<<grid, 256, 0, lm->stream>>>(m, hm->d, display);
-        else k_commit<1, 1><<<grid, 256, 0, lm->stream>>>(m, hm->d, display);
+        k_commit<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, display, hm->blk_list, hm->blk_count);
     }
     k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->stats_host);
-    lm->launches += 5;
+    lm->launches += 6;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
