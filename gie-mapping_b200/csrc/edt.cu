@@ -279,6 +279,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     const int X = m.X, Z = m.Z, S = m.max_width;
     const size_t slice = (size_t)X * m.Y;
     const int ns = __ldg(n_slices);
+    const int3 wr0 = m.pvt - m.upvt;   // local coords -> wave-range coords
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(work_counter, 1);
@@ -314,14 +315,19 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             int k = __ldg(&slice_list[j]);
             envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
         }
-        // backward (local_edt_core.h:169-192)
+        // backward (local_edt_core.h:169-192).  Besides _aux / _coc_idx_aux the sweep also writes the (dist, wave-range coc
+        // id) pair every voxel starts the merge with (the UNKNOWN-voxel half of MarkLimitedObserve, unify_helper.cuh:201-273),
+        // which saves a 17 B/voxel pass over the volume; k_mark then only patches known voxels.
         int c = __ldg(&cxy[base + (size_t)top.s * slice]);
         for (int u = Z - 1; u >= 0; u--) {
             int d = u - top.s;
             if (valid) {
                 size_t o = base + (size_t)u * slice;
-                __stcs(&m.aux[o], d * d + top.h);
+                const int dist = d * d + top.h;
+                __stcs(&m.aux[o], dist);
                 __stcs(&m.coc_aux[o], (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22));
+                int3 wr = make_int3((c & 0xffff) + wr0.x, (c >> 16) + wr0.y, top.s + wr0.z);
+                __stcs(&m.pair[o], gie_inside_wr(wr) ? gie_mk_pair(dist, gie_wr2id(wr)) : gie_mk_pair(GIE_EMPTY_VALUE, GIE_INVALID_ID_STALE));
             }
             if (u == top.t) {
                 q--;

@@ -107,8 +107,11 @@ __device__ __forceinline__ bool q_push(T *q, int *cnt, int cap, T v, int *status
 // MarkLimitedObserve (unify_helper.cuh:201-273).  Each thread owns VEC consecutive voxels along x (vector loads/stores),
 // grid-stride over a grid sized to the SM count.  D4: UNKNOWN voxels get their batch values instead of stale memory.
 template <int VEC>
-__global__ void __launch_bounds__(256) k_mark(LocDev m, HashDev h)
+__global__ void __launch_bounds__(256) k_mark(LocDev m, HashDev h, const int *__restrict__ n_slices)
 {
+    // Full-volume form, only needed while the volume holds no obstacle at all ("sees nothing" sentinels everywhere);
+    // otherwise the z sweep has written every voxel's starting pair and k_mark_blocks patches the known voxels.
+    if (__ldcg(n_slices) > 0) return;
     const int nq = m.N / VEC;
     const int mw = m.max_width;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
@@ -187,6 +190,33 @@ __device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev
     int3 k = make_int3(ti % h.tab_dim.x, (ti / h.tab_dim.x) % h.tab_dim.y, ti / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
     c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - m.pvt;
     return gie_inside_loc(m, c);
+}
+
+// MarkLimitedObserve (unify_helper.cuh:201-273) for the known voxels: where the batch EDT found something farther than the
+// distance the global map remembers to an obstacle that has left the volume, keep the remembered one.
+__global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ n_slices, const int *__restrict__ list,
+                                                     const int *__restrict__ count)
+{
+    if (__ldcg(n_slices) == 0) return;   // k_mark handles the obstacle-free volume
+    const int n = __ldcg(count);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int ti = __ldcg(&list[b]);
+        const int blk = __ldcg(&h.btab[ti]);
+        for (int v = threadIdx.x; v < 512; v += blockDim.x) {
+            int3 c;
+            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            const int id = gie_lidx(m, c);
+            if (m.glb_type[id] == GIE_VOX_UNKNOWN) continue;
+            const size_t vi = (size_t)blk * 512 + v;
+            const int dist_new = m.aux[id], dist_old = h.dist_sq[vi];
+            if (!(dist_new > dist_old)) continue;
+            const int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
+            if (gie_inside_loc(m, coc_buf_old)) continue;
+            const int3 wr = coc_buf_old + m.pvt - m.upvt;
+            if (!gie_inside_wr(wr)) { m.pair[id] = gie_mk_pair(GIE_EMPTY_VALUE, GIE_INVALID_ID_STALE); m.aux[id] = GIE_EMPTY_VALUE; }
+            else { m.pair[id] = gie_mk_pair(dist_old, gie_wr2id(wr)); m.aux[id] = dist_old; }
+        }
+    }
 }
 
 // obtainFrontiers (unify_helper.cuh:275-446) for one known voxel.  pair[] is read-only here: a lowered own pair (frontier C
@@ -847,8 +877,10 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
         const int entries = (int)hm->tab_entries;
         k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(m, hm->d, entries, hm->blk_list, hm->blk_count);
-        if (vec == 4) k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d);
-        else k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d);
+        const int *n_slices = lm->edt_meta + 2 * m.Z;
+        if (vec == 4) k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d, n_slices);
+        else k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d, n_slices);
+        k_mark_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, n_slices, hm->blk_list, hm->blk_count);
         k_frontiers<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
     }
     {
@@ -880,7 +912,7 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         k_commit<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, display, hm->blk_list, hm->blk_count);
     }
     k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->stats_host);
-    lm->launches += 6;
+    lm->launches += 7;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
