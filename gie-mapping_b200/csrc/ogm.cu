@@ -87,17 +87,41 @@ __global__ void k_pc_free(LocDev m, const float *__restrict__ pts, int n, float 
     if (sy != 0) { float b = (float)p0i.y * m.w + (float)sy * m.w * 0.5f; tmy = (b - p0.y) / dy; tdy = m.w / fabsf(dy); }
     if (sz != 0) { float b = (float)p0i.z * m.w + (float)sz * m.w * 0.5f; tmz = (b - p0.z) / dz; tdz = m.w / fabsf(dz); }
     int3 cur = p0i;
+    // The walk itself is pure arithmetic; what made a step slow was the dependent load of inst_type that decides whether the
+    // ray stops.  inst_type is read-only in this kernel, so the DDA runs K steps ahead, the K loads are issued together, and
+    // the decisions (stop at the first OCCUPIED voxel, otherwise decrement) are then applied in order — same voxels, same
+    // order, same float operations as the one-step-at-a-time loop of ray_cast.h:104-143.
+    constexpr int K = 8;
     for (;;) {
-        // comparison tree of ray_cast.h:107-114, reproduced literally
-        if (tmx < tmy) {
-            if (tmx < tmz) { cur.x += sx; tmx += tdx; } else { cur.z += sz; tmz += tdz; }
-        } else {
-            if (tmy < tmz) { cur.y += sy; tmy += tdy; } else { cur.z += sz; tmz += tdz; }
+        int ids[K];
+        int nsteps = 0;
+        bool finished = false;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (finished) { ids[j] = -1; continue; }
+            // comparison tree of ray_cast.h:107-114, reproduced literally
+            if (tmx < tmy) {
+                if (tmx < tmz) { cur.x += sx; tmx += tdx; } else { cur.z += sz; tmz += tdz; }
+            } else {
+                if (tmy < tmz) { cur.y += sy; tmy += tdy; } else { cur.z += sz; tmz += tdz; }
+            }
+            int3 loc = cur - m.pvt;
+            ids[j] = gie_inside_loc(m, loc) ? gie_lidx(m, loc) : -1;
+            nsteps = j + 1;
+            float d = fminf(fminf(tmx, tmy), tmz);
+            finished = eq3(cur, p1i) || d > max_length || d > len;
         }
-        if (!clear_ray_loc(m, cur - m.pvt)) break;
-        if (eq3(cur, p1i)) break;
-        float d = fminf(fminf(tmx, tmy), tmz);
-        if (d > max_length || d > len) break;
+        int8_t t[K];
+#pragma unroll
+        for (int j = 0; j < K; j++) t[j] = (j < nsteps && ids[j] >= 0) ? m.inst_type[ids[j]] : (int8_t)GIE_VOX_UNKNOWN;
+        bool hit = false;
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+            if (hit || j >= nsteps || ids[j] < 0) continue;
+            if (t[j] == GIE_VOX_OCCUPIED) hit = true;            // clearRayLoc returns false: the ray stops here
+            else atomicAdd(&m.ray_count[ids[j]], -1);            // result unused -> RED
+        }
+        if (hit || finished) break;
     }
 }
 
