@@ -52,76 +52,100 @@ __global__ void k_pc_register(LocDev m, const float *__restrict__ pts, int n)
     }
 }
 
-// clearRayLoc (pntcld_raycast.cu:9-18) with the bounds-checked accessors of local_batch.h:302-349
-__device__ __forceinline__ bool clear_ray_loc(const LocDev &m, int3 loc)
-{
-    bool in = gie_inside_loc(m, loc);
-    if (!in) return true;
-    int id = gie_lidx(m, loc);
-    if (m.inst_type[id] != GIE_VOX_OCCUPIED) {
-        atomicAdd(&m.ray_count[id], -1);   // result unused -> RED
-        return true;
-    }
-    return false;
-}
-
 // freeLocObs (pntcld_raycast.cu:67-80) + RAY::rayCastLoc (ray_cast.h:57-144)
-__global__ void k_pc_free(LocDev m, const float *__restrict__ pts, int n, float max_length)
+//
+// Every ray starts at the sensor, so the voxels around the origin are decremented by all ~64 k rays: tens of thousands of
+// same-address atomics that serialise in one L2 slice.  Each CTA therefore accumulates the decrements that fall into a
+// WIN^3 window around the origin voxel in shared memory and flushes the window once at the end (sums commute, the result
+// is identical); decrements outside the window go straight to global memory.
+constexpr int RAY_WIN = 16;
+__global__ void __launch_bounds__(128) k_pc_free(LocDev m, const float *__restrict__ pts, int n, float max_length)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
-    float3 p1 = se3_apply(m.L2G, p);
-    float3 p0 = m.origin;
-    int3 p0i = pos2coord(m, p0), p1i = pos2coord(m, p1);
-    clear_ray_loc(m, p0i - m.pvt);
-    if (eq3(p0i, p1i)) return;
-    float dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;
-    float len = sqrtf(dx * dx + dy * dy + dz * dz);
-    dx = dx / len; dy = dy / len; dz = dz / len;
-    int sx = dx > 0.0f ? 1 : (dx < 0.0f ? -1 : 0);
-    int sy = dy > 0.0f ? 1 : (dy < 0.0f ? -1 : 0);
-    int sz = dz > 0.0f ? 1 : (dz < 0.0f ? -1 : 0);
-    float tmx = FLT_MAX, tmy = FLT_MAX, tmz = FLT_MAX, tdx = FLT_MAX, tdy = FLT_MAX, tdz = FLT_MAX;
-    if (sx != 0) { float b = (float)p0i.x * m.w + (float)sx * m.w * 0.5f; tmx = (b - p0.x) / dx; tdx = m.w / fabsf(dx); }
-    if (sy != 0) { float b = (float)p0i.y * m.w + (float)sy * m.w * 0.5f; tmy = (b - p0.y) / dy; tdy = m.w / fabsf(dy); }
-    if (sz != 0) { float b = (float)p0i.z * m.w + (float)sz * m.w * 0.5f; tmz = (b - p0.z) / dz; tdz = m.w / fabsf(dz); }
-    int3 cur = p0i;
-    // The walk itself is pure arithmetic; what made a step slow was the dependent load of inst_type that decides whether the
-    // ray stops.  inst_type is read-only in this kernel, so the DDA runs K steps ahead, the K loads are issued together, and
-    // the decisions (stop at the first OCCUPIED voxel, otherwise decrement) are then applied in order — same voxels, same
-    // order, same float operations as the one-step-at-a-time loop of ray_cast.h:104-143.
-    constexpr int K = 8;
-    for (;;) {
-        int ids[K];
-        int nsteps = 0;
-        bool finished = false;
+    __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
+    for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) win[k] = 0;
+    __syncthreads();
+    const float3 p0 = m.origin;
+    const int3 p0i = pos2coord(m, p0);
+    const int3 worg = p0i - make_int3(RAY_WIN / 2, RAY_WIN / 2, RAY_WIN / 2);   // global coords of window cell (0,0,0)
+    // decrement of an in-volume voxel given its GLOBAL coords
+    auto dec = [&](int3 g, int id) {
+        int3 q = g - worg;
+        if ((unsigned)q.x < RAY_WIN && (unsigned)q.y < RAY_WIN && (unsigned)q.z < RAY_WIN) atomicAdd(&win[(q.z * RAY_WIN + q.y) * RAY_WIN + q.x], -1);
+        else atomicAdd(&m.ray_count[id], -1);   // result unused -> RED
+    };
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = i < n;
+    int3 p1i = p0i;
+    float3 p1 = p0;
+    if (active) {
+        float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+        p1 = se3_apply(m.L2G, p);
+        p1i = pos2coord(m, p1);
+        // first `opr` on the origin voxel (ray_cast.h:70-72; clearRayLoc pntcld_raycast.cu:9-18)
+        int3 loc = p0i - m.pvt;
+        if (gie_inside_loc(m, loc)) {
+            int id = gie_lidx(m, loc);
+            if (m.inst_type[id] != GIE_VOX_OCCUPIED) dec(p0i, id);
+        }
+        if (eq3(p0i, p1i)) active = false;
+    }
+    if (active) {
+        float dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;
+        float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        dx = dx / len; dy = dy / len; dz = dz / len;
+        int sx = dx > 0.0f ? 1 : (dx < 0.0f ? -1 : 0);
+        int sy = dy > 0.0f ? 1 : (dy < 0.0f ? -1 : 0);
+        int sz = dz > 0.0f ? 1 : (dz < 0.0f ? -1 : 0);
+        float tmx = FLT_MAX, tmy = FLT_MAX, tmz = FLT_MAX, tdx = FLT_MAX, tdy = FLT_MAX, tdz = FLT_MAX;
+        if (sx != 0) { float b = (float)p0i.x * m.w + (float)sx * m.w * 0.5f; tmx = (b - p0.x) / dx; tdx = m.w / fabsf(dx); }
+        if (sy != 0) { float b = (float)p0i.y * m.w + (float)sy * m.w * 0.5f; tmy = (b - p0.y) / dy; tdy = m.w / fabsf(dy); }
+        if (sz != 0) { float b = (float)p0i.z * m.w + (float)sz * m.w * 0.5f; tmz = (b - p0.z) / dz; tdz = m.w / fabsf(dz); }
+        int3 cur = p0i;
+        // The walk itself is pure arithmetic; what made a step slow was the dependent load of inst_type that decides whether
+        // the ray stops.  inst_type is read-only in this kernel, so the DDA runs K steps ahead, the K loads are issued
+        // together, and the decisions (stop at the first OCCUPIED voxel, otherwise decrement) are then applied in order —
+        // same voxels, same order, same float operations as the one-step-at-a-time loop of ray_cast.h:104-143.
+        constexpr int K = 8;
+        for (;;) {
+            int ids[K];
+            int3 gs[K];
+            int nsteps = 0;
+            bool finished = false;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            if (finished) { ids[j] = -1; continue; }
-            // comparison tree of ray_cast.h:107-114, reproduced literally
-            if (tmx < tmy) {
-                if (tmx < tmz) { cur.x += sx; tmx += tdx; } else { cur.z += sz; tmz += tdz; }
-            } else {
-                if (tmy < tmz) { cur.y += sy; tmy += tdy; } else { cur.z += sz; tmz += tdz; }
+            for (int j = 0; j < K; j++) {
+                if (finished) { ids[j] = -1; gs[j] = cur; continue; }
+                // comparison tree of ray_cast.h:107-114, reproduced literally
+                if (tmx < tmy) {
+                    if (tmx < tmz) { cur.x += sx; tmx += tdx; } else { cur.z += sz; tmz += tdz; }
+                } else {
+                    if (tmy < tmz) { cur.y += sy; tmy += tdy; } else { cur.z += sz; tmz += tdz; }
+                }
+                int3 loc = cur - m.pvt;
+                ids[j] = gie_inside_loc(m, loc) ? gie_lidx(m, loc) : -1;
+                gs[j] = cur;
+                nsteps = j + 1;
+                float d = fminf(fminf(tmx, tmy), tmz);
+                finished = eq3(cur, p1i) || d > max_length || d > len;
             }
-            int3 loc = cur - m.pvt;
-            ids[j] = gie_inside_loc(m, loc) ? gie_lidx(m, loc) : -1;
-            nsteps = j + 1;
-            float d = fminf(fminf(tmx, tmy), tmz);
-            finished = eq3(cur, p1i) || d > max_length || d > len;
-        }
-        int8_t t[K];
+            int8_t t[K];
 #pragma unroll
-        for (int j = 0; j < K; j++) t[j] = (j < nsteps && ids[j] >= 0) ? m.inst_type[ids[j]] : (int8_t)GIE_VOX_UNKNOWN;
-        bool hit = false;
+            for (int j = 0; j < K; j++) t[j] = (j < nsteps && ids[j] >= 0) ? m.inst_type[ids[j]] : (int8_t)GIE_VOX_UNKNOWN;
+            bool hit = false;
 #pragma unroll
-        for (int j = 0; j < K; j++) {
-            if (hit || j >= nsteps || ids[j] < 0) continue;
-            if (t[j] == GIE_VOX_OCCUPIED) hit = true;            // clearRayLoc returns false: the ray stops here
-            else atomicAdd(&m.ray_count[ids[j]], -1);            // result unused -> RED
+            for (int j = 0; j < K; j++) {
+                if (hit || j >= nsteps || ids[j] < 0) continue;
+                if (t[j] == GIE_VOX_OCCUPIED) hit = true;            // clearRayLoc returns false: the ray stops here
+                else dec(gs[j], ids[j]);
+            }
+            if (hit || finished) break;
         }
-        if (hit || finished) break;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) {
+        int v = win[k];
+        if (v == 0) continue;
+        int3 loc = worg + make_int3(k % RAY_WIN, (k / RAY_WIN) % RAY_WIN, k / (RAY_WIN * RAY_WIN)) - m.pvt;
+        atomicAdd(&m.ray_count[gie_lidx(m, loc)], v);   // only in-volume voxels were accumulated
     }
 }
 
