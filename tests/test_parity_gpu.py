@@ -394,3 +394,105 @@ def test_cuda_engine_vs_reference_golden(gie, path):
         assert exact_frames >= 1
     finally:
         mp.close()
+
+
+def test_empty_and_degenerate_inputs(gie, oracle):
+    """Empty scan (0 points), a scan with every ray outside the volume, an all-NaN 2-D scan and an all-NaN depth image:
+    same result as the oracle, no device error, and the map keeps working afterwards."""
+    cfg = gie.scenes.small_config("cfg4", (48, 48, 24), cutoff_grids_sq=64)
+    frames = gie.scenes.make_frames(cfg, 4, dynamic=True)
+    frames[1] = dict(frames[1], points=np.zeros((0, 3), np.float32))
+    frames[2] = dict(frames[2], points=(frames[2]["points"] * 0 + np.array([500.0, 0, 0], np.float32)))
+    mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+    try:
+        for k, f in enumerate(frames):
+            mp.publishMap(f)
+            om.publishMap(f)
+            _cmp_frame(gie, mp, om, f"degenerate point cloud frame {k}")
+    finally:
+        mp.close()
+        om.close()
+    for name, key in [("cfg1", "scan"), ("cfg3", "depth")]:
+        cfg = gie.scenes.small_config(name, (64, 64, 16 if name == "cfg1" else 32), cutoff_grids_sq=100)
+        frames = gie.scenes.make_frames(cfg, 3)
+        frames[1] = dict(frames[1])
+        frames[1][key] = np.full_like(frames[1][key], np.nan)
+        mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)
+        try:
+            for k, f in enumerate(frames):
+                mp.publishMap(f)
+                om.publishMap(f)
+                _cmp_frame(gie, mp, om, f"{name} NaN frame {k}")
+        finally:
+            mp.close()
+            om.close()
+
+
+def test_error_paths(gie):
+    """Status codes instead of the reference's exit(1) / assert / throw: oversize volume, bad arguments, exhausted block pool."""
+    with pytest.raises(gie.GieError, match="-5"):
+        gie.LocMap(0.1, (2048, 64, 64))                       # "Local map size too big!!!" (local_batch.h:54-58)
+    with pytest.raises(gie.GieError):
+        gie.LocMap(-1.0, (32, 32, 32))
+    cfg = gie.scenes.small_config("cfg4", (48, 48, 24), cutoff_grids_sq=64)
+    cfg["block_max"] = 8                                      # the scan touches far more than 8 blocks
+    frames = gie.scenes.make_frames(cfg, 1)
+    mp = gie.Mapper(cfg)
+    try:
+        mp.publishMap(frames[0])
+        with pytest.raises(gie.GieError, match="-3"):         # throw "out of block memory" (blockalloc.h:56-58)
+            mp.hash_map.sync()
+    finally:
+        mp.close()
+    lm = gie.LocMap(0.1, (32, 32, 32))
+    try:
+        with pytest.raises(gie.GieError):
+            lm.device_ptr(99)
+    finally:
+        lm.close()
+
+
+def test_batch_edt_maximum_size_tie_rules(gie):
+    """The largest volume the coc codec admits (1024 x 1024 x 1022, 1.07 G voxels) with 64 obstacles placed on a lattice that
+    produces many exact ties; 200 k sampled voxels against brute force with the reference's tie rule: smallest distance,
+    then smallest obstacle z, then smallest obstacle x, then LARGEST obstacle y."""
+    import ctypes as C
+    X, Y, Z = 1024, 1024, 1022
+    rng = np.random.RandomState(23)
+    obs = np.stack([rng.randint(0, 16, 64) * 64 + 10, rng.randint(0, 16, 64) * 64 + 10, rng.randint(0, 16, 64) * 63 + 5], axis=1)
+    obs = np.unique(obs, axis=0)
+    lm = gie.LocMap(0.1, (X, Y, Z), cutoff_grids_sq=2500)
+    try:
+        t = np.ones((Z, Y, X), np.int8)
+        t[obs[:, 2], obs[:, 1], obs[:, 0]] = 2
+        lm.upload_glb_type(t)
+        del t
+        lm.batchEDTUpdate()
+        ptr_a, _ = lm.device_ptr(gie.ARR_AUX)
+        ptr_c, _ = lm.device_ptr(gie.ARR_COC_AUX)
+        import torch
+        from gie_mapping_b200 import sharded
+        aux = sharded.device_tensor(lm, gie.ARR_AUX, (Z, Y, X))
+        coc = sharded.device_tensor(lm, gie.ARR_COC_AUX, (Z, Y, X))
+        n = 200000
+        sx, sy, sz = rng.randint(0, X, n), rng.randint(0, Y, n), rng.randint(0, Z, n)
+        # bias half of the samples onto lattice mid-planes where ties are certain
+        sx[: n // 2] = (sx[: n // 2] // 64) * 64 + 42
+        sy[: n // 4] = (sy[: n // 4] // 64) * 64 + 42
+        idx = torch.from_numpy((sz.astype(np.int64) * Y + sy) * X + sx).cuda()
+        d = aux.view(-1)[idx].cpu().numpy().astype(np.int64)
+        c = coc.view(-1)[idx].cpu().numpy().astype(np.int64)
+    finally:
+        lm.close()
+    dx = sx[:, None] - obs[None, :, 0]
+    dy = sy[:, None] - obs[None, :, 1]
+    dz = sz[:, None] - obs[None, :, 2]
+    dist = (dx * dx + dy * dy + dz * dz).astype(np.int64)
+    # lexicographic key: dist, obstacle z, obstacle x, -obstacle y
+    key = ((dist * 1024 + obs[None, :, 2]) * 1024 + obs[None, :, 0]) * 1024 + (1023 - obs[None, :, 1])
+    best = key.argmin(axis=1)
+    assert np.array_equal(d, dist[np.arange(n), best])
+    exp = obs[best]
+    assert np.array_equal(c & 0x7ff, exp[:, 0]) and np.array_equal((c >> 11) & 0x7ff, exp[:, 1]) and np.array_equal((c >> 22) & 0x3ff, exp[:, 2])
+    ties = (np.sort(dist, axis=1)[:, 0] == np.sort(dist, axis=1)[:, 1]).sum()
+    assert ties > 1000, f"only {ties} tied samples: the test lost its point"
