@@ -23,14 +23,17 @@
 //                 coalesced; gathers (cocx,cocy) of the winning slice and writes the final packed result.
 // Persistent CTAs (a multiple of the SM count) pull work items from an atomic counter.
 #include "engine.h"
+#include <algorithm>
 
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
 constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
 constexpr int RING = 16;      // stack entries per lane kept in shared memory
-constexpr int XS_SMEM_INTS_PER_WARP = 2 * 32 * 17 + 2 * RING * 32;
-constexpr int XS_SMEM_BYTES = WARPS_PER_CTA * XS_SMEM_INTS_PER_WARP * 4;
+constexpr int XB = 4;          // warps per x-sweep CTA = candidate bands = output x ranges of one (slice, 32 rows) item
+constexpr int XS_TILE_INTS = 2 * 32 * 17, XS_RING_INTS = 2 * RING * 32;
+constexpr int XS_SMEM_INTS_PER_WARP = XS_TILE_INTS + XS_RING_INTS + 64;   // tiles, stack ring, per-lane (q, base)
+constexpr int XS_SMEM_BYTES = XB * XS_SMEM_INTS_PER_WARP * 4;
 
 // y pass, step 1: OCCUPIED bits of 32 consecutive y per (z, wy, x) -> low word of ytab.  One thread per word, x fastest:
 // 4 M independent threads at 512^3, each with 32 coalesced byte loads in flight.
@@ -182,27 +185,71 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3)
+// read-only view of the envelope stack another warp of the CTA has built (entries are private to a lane)
+struct StackView {
+    const int *sh, *sb;
+    const uint2 *g;
+    int base, q;
+    __device__ __forceinline__ Top read(int i) const
+    {
+        int hh, bb;
+        if (i >= base) { int sl = (i & (RING - 1)) * 32; hh = sh[sl]; bb = sb[sl]; }
+        else { uint2 v = g[i * 32]; hh = (int)v.x; bb = (int)v.y; }
+        Top e;
+        e.h = hh; e.s = bb & 0x3ff; e.t = (bb >> 10) & 0x3ff; e.cy = bb >> 20;
+        return e;
+    }
+};
+// push the entries of b (all to the right of everything on the stack) onto the stack: the same sequential algorithm, run on the
+// candidates that survived inside their own band
+__device__ __forceinline__ void merge_into(int &q, Top &top, LaneStack &st, const StackView &b, int L)
+{
+    const int qmax = __reduce_max_sync(0xffffffffu, b.q);
+    for (int i = 0; i <= qmax; i++)
+        if (i <= b.q) {
+            Top e = b.read(i);
+            envelope_push(e.s, e.h, e.cy, L, q, top, st);
+        }
+}
+
+// x sweep (EDTphase2, local_edt_core.h:84-135).  One CTA of XB warps per (obstacle-bearing slice, 32 consecutive rows); lane =
+// row.  A slice holds few such items (36 slices x 16 row groups in the headline scene), so a single warp per item left the
+// GPU running one long dependent scan per scheduler.  Here the real columns of the slice are cut into XB bands; every warp
+// builds the lower envelope of its band, the band envelopes are merged pairwise with the same push step (a candidate that is
+// not on its band's envelope cannot be on the row's), and the backward pass is cut into XB ranges of x, each warp reading
+// the final stack of warp 0 and emitting through its own 32x16 tile.
+__global__ void __launch_bounds__(XB * 32)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
              int32_t *__restrict__ g2, int32_t *__restrict__ cxy, uint2 *__restrict__ scratch, int L,
              int *__restrict__ work_counter)
 {
-    extern __shared__ int xs_smem[];   // per warp: tile_g[32][17], tile_c[32][17], ring[2][RING][32]
+    extern __shared__ int xs_smem[];   // per warp: tile_g[32][17], tile_c[32][17], ring[2][RING][32], q[32], base[32]
+    __shared__ int s_item;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int gwarp = blockIdx.x * WARPS_PER_CTA + wid;
     int *wsm = xs_smem + wid * XS_SMEM_INTS_PER_WARP;
     int (*tile_g)[17] = (int (*)[17])wsm;
     int (*tile_c)[17] = (int (*)[17])(wsm + 32 * 17);
+    auto ring_of = [&](int w) { return xs_smem + w * XS_SMEM_INTS_PER_WARP + XS_TILE_INTS; };
+    auto meta_of = [&](int w) { return xs_smem + w * XS_SMEM_INTS_PER_WARP + XS_TILE_INTS + XS_RING_INTS; };
+    auto scratch_of = [&](int w) { return scratch + (size_t)(blockIdx.x * XB + w) * L * 32 + lane; };
+    auto view_of = [&](int w) {
+        StackView v;
+        v.sh = ring_of(w) + lane; v.sb = v.sh + RING * 32; v.g = scratch_of(w);
+        v.q = meta_of(w)[lane]; v.base = meta_of(w)[32 + lane];
+        return v;
+    };
     LaneStack st;
-    st.sh = wsm + 2 * 32 * 17 + lane; st.sb = st.sh + RING * 32;
-    st.g = scratch + (size_t)gwarp * L * 32 + lane;
+    st.sh = ring_of(wid) + lane; st.sb = st.sh + RING * 32;
+    st.g = scratch_of(wid);
     const int X = m.X, Y = m.Y;
     const int n_items = __ldg(n_slices) * WY;
+    const int chunk = (((X + XB - 1) / XB) + 15) & ~15;   // x range of a warp in the backward pass, multiple of the tile width
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        __syncthreads();   // the previous item's stacks are no longer read
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
         if (item >= n_items) break;
         const int zi = item / WY, wy = item - zi * WY;
         const int z = __ldg(&slice_list[zi]);
@@ -210,16 +257,18 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
         const unsigned long long *trow = ytab + ((size_t)z * WY + wy) * X;
         const int *cols = col_list + (size_t)z * X;
         const int nc = __ldg(&n_cols[z]);
+        // ---- forward pass over this warp's band of the real columns
+        const int jb = (int)((long long)nc * wid / XB), je = (int)((long long)nc * (wid + 1) / XB);
         int q = -1;
         Top top{0, 0, 0, 0};
         st.base = 0;
         const uint32_t lomask = 0xffffffffu >> (31 - lane);
-        for (int j0 = 0; j0 < nc; j0 += 4) {
+        for (int j0 = jb; j0 < je; j0 += 4) {
             // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
             int uu[4], gg[4], cc[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                int j = min(j0 + k, nc - 1);
+                int j = min(j0 + k, je - 1);
                 int u = __ldg(&cols[j]);
                 unsigned long long e = __ldg(&trow[u]);
                 uint32_t w = (uint32_t)e;
@@ -234,32 +283,52 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
             }
 #pragma unroll
             for (int k = 0; k < 4; k++)
-                if (j0 + k < nc) envelope_push(uu[k], gg[k], cc[k], X, q, top, st);
+                if (j0 + k < je) envelope_push(uu[k], gg[k], cc[k], X, q, top, st);
         }
-        // EDTphase2 backward loop (local_edt_core.h:116-134), emitted through a 32 x 16 tile
-        for (int u = X - 1; u >= 0; u--) {
-            int d = u - top.s;
-            tile_g[lane][u & 15] = d * d + top.h;
-            tile_c[lane][u & 15] = top.s | (top.cy << 16);
-            if (u == top.t) {
-                q--;
-                if (q >= 0) top = st.get(q);
-            }
-            if ((u & 15) == 0) {
-                __syncwarp();
-                const int col = lane & 15, r0 = lane >> 4;
-                const int xx = u + col;
-                int32_t *pg = g2 + ((size_t)z * Y + wy * 32 + r0) * X + xx;
-                int32_t *pc = cxy + ((size_t)z * Y + wy * 32 + r0) * X + xx;
-#pragma unroll 4
-                for (int i = 0; i < 16; i++) {
-                    int r = 2 * i + r0;
-                    if (wy * 32 + r < Y && xx < X) {
-                        pg[(size_t)2 * i * X] = tile_g[r][col];
-                        pc[(size_t)2 * i * X] = tile_c[r][col];
-                    }
+        meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
+        // ---- merge the band envelopes: (0 <- 1), (2 <- 3), then (0 <- 2)
+        __syncthreads();
+        if ((wid & 1) == 0) {
+            merge_into(q, top, st, view_of(wid + 1), X);
+            meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            merge_into(q, top, st, view_of(2), X);
+            meta_of(0)[lane] = q; meta_of(0)[32 + lane] = st.base;
+        }
+        __syncthreads();
+        // ---- EDTphase2 backward loop (local_edt_core.h:116-134) over this warp's x range, emitted through a 32 x 16 tile
+        const int x_lo = wid * chunk, x_hi = min(X, x_lo + chunk) - 1;
+        if (x_lo <= x_hi) {
+            const StackView fin = view_of(0);
+            int qq = fin.q;
+            Top e = fin.read(qq);
+            while (e.t > x_hi) { qq--; e = fin.read(qq); }   // the bottom entry starts at 0, so this ends
+            for (int u = x_hi; u >= x_lo; u--) {
+                int d = u - e.s;
+                tile_g[lane][u & 15] = d * d + e.h;
+                tile_c[lane][u & 15] = e.s | (e.cy << 16);
+                if (u == e.t) {
+                    qq--;
+                    if (qq >= 0) e = fin.read(qq);
                 }
-                __syncwarp();
+                if ((u & 15) == 0) {
+                    __syncwarp();
+                    const int col = lane & 15, r0 = lane >> 4;
+                    const int xx = u + col;
+                    int32_t *pg = g2 + ((size_t)z * Y + wy * 32 + r0) * X + xx;
+                    int32_t *pc = cxy + ((size_t)z * Y + wy * 32 + r0) * X + xx;
+#pragma unroll 4
+                    for (int i = 0; i < 16; i++) {
+                        int r = 2 * i + r0;
+                        if (wy * 32 + r < Y && xx < X) {
+                            pg[(size_t)2 * i * X] = tile_g[r][col];
+                            pc[(size_t)2 * i * X] = tile_c[r][col];
+                        }
+                    }
+                    __syncwarp();
+                }
             }
         }
     }
@@ -354,7 +423,12 @@ int gie_edt_prepare(gie_locmap *lm)
     int need = (n_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (need < ctas) ctas = need;   // small volumes: no idle persistent CTAs
     lm->edt_ctas = ctas;
-    lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
+    // x sweep: one CTA of XB warps per (slice, 32 rows) item, as many as can be resident
+    int xs_per_sm = 1;
+    GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep, XB * 32, XS_SMEM_BYTES));
+    if (xs_per_sm < 1) xs_per_sm = 1;
+    lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * WY);
+    lm->stack_scratch_entries = (size_t)std::max(ctas * WARPS_PER_CTA, lm->xs_ctas * XB) * L * 32;
     GIE_CUDA_CHECK(cudaMalloc(&lm->stack_scratch, lm->stack_scratch_entries * 8));
     GIE_CUDA_CHECK(cudaMalloc(&lm->work_counters, 4 * sizeof(int)));
     GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM_BYTES));
@@ -373,8 +447,8 @@ int gie_launch_edt_xy(gie_locmap *lm)
     k_edt_ybits<<<dim3((m.X + 127) / 128, WY, m.Z), 128, 0, lm->stream>>>(m, lm->ytab, WY);
     k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
-    k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                      lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
+    k_edt_xsweep<<<lm->xs_ctas, XB * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                              lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
     lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -410,9 +484,8 @@ int gie_launch_batch_edt(gie_locmap *lm)
     }
     {
         StageTimer t(lm, GIE_ST_EDT_X);
-        k_edt_xsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                          lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L,
-                                                                          lm->work_counters + 0);
+        k_edt_xsweep<<<lm->xs_ctas, XB * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                                  lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_Z);

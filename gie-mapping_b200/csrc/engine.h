@@ -18,7 +18,8 @@ struct gie_locmap {
     int *edt_meta = nullptr;              // n_cols[Z], slice_list[Z], n_slices
     unsigned long long *stack_scratch = nullptr;
     size_t stack_scratch_entries = 0;
-    int edt_ctas = 0;                     // persistent grid of the sweep kernels
+    int edt_ctas = 0;                     // persistent grid of the z sweep
+    int xs_ctas = 0;                      // persistent grid of the x sweep (4 warps per CTA)
     int *work_counters = nullptr;         // device: [4]
     // staging for *_host entry points
     float *stage_dev = nullptr;
