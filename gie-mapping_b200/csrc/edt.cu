@@ -286,16 +286,14 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
                 if (j0 + k < je) envelope_push(uu[k], gg[k], cc[k], X, q, top, st);
         }
         meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
-        // ---- merge the band envelopes: (0 <- 1), (2 <- 3), then (0 <- 2)
-        __syncthreads();
-        if ((wid & 1) == 0) {
-            merge_into(q, top, st, view_of(wid + 1), X);
-            meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
-        }
-        __syncthreads();
-        if (wid == 0) {
-            merge_into(q, top, st, view_of(2), X);
-            meta_of(0)[lane] = q; meta_of(0)[32 + lane] = st.base;
+        // ---- merge the band envelopes pairwise: (0 <- 1), (2 <- 3), ... then (0 <- 2), (4 <- 6), ... until warp 0 holds the row's
+#pragma unroll
+        for (int stride = 1; stride < XB; stride <<= 1) {
+            __syncthreads();
+            if ((wid & (2 * stride - 1)) == 0 && wid + stride < XB) {
+                merge_into(q, top, st, view_of(wid + stride), X);
+                meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
+            }
         }
         __syncthreads();
         // ---- EDTphase2 backward loop (local_edt_core.h:116-134) over this warp's x range, emitted through a 32 x 16 tile
