@@ -65,6 +65,7 @@ struct HashDev {
     unsigned long long *pair;
     // per-frame dense block table around the local volume (one hash probe per block, not per voxel)
     int32_t *btab;
+    uint8_t *touched;          // per table entry: a sensor kernel wrote a counter / a type inside this block this frame
     uint8_t *dirty;            // per block: changed since the last gie_hashmap_stream_changed (reference: stream_VB_keys_D)
     int3 tab_org;   // block coords of table entry (0,0,0)
     int3 tab_dim;
@@ -169,4 +170,7 @@ __device__ __forceinline__ int gie_tab_index(const HashDev &h, int3 glb)
     int3 t = gie_vb_key(glb) - h.tab_org;
     return (t.z * h.tab_dim.y + t.y) * h.tab_dim.x + t.x;
 }
+// the sensor kernels record which blocks they wrote into (plain byte stores of the same value: no atomics needed); the merge
+// then visits only touched or allocated blocks instead of streaming the whole volume
+__device__ __forceinline__ void gie_touch_block(const HashDev &h, int3 glb) { h.touched[gie_tab_index(h, glb)] = 1; }
 #endif

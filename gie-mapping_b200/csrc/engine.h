@@ -53,6 +53,8 @@ struct gie_hashmap {
     int32_t *decA_flags = nullptr;
     uint32_t *snap_id = nullptr;  // per-queue-slot snapshot for waves B/C
     int wave_ctas = 0;
+    int *merge_list = nullptr;    // table indices of the touched or allocated blocks that intersect the volume (per OGM merge)
+    int *merge_count = nullptr;
     int *blk_list = nullptr;      // table indices of the allocated blocks that intersect the local volume (per merge)
     int *blk_count = nullptr;
     int merge_epoch = 0;          // merges done so far; the seed mark of m.wave_layer (memset to 0 at creation)

@@ -68,8 +68,14 @@ __device__ __forceinline__ void set_occ_val(uint8_t &occ, int8_t &type, float va
     type = (occ > thresh) ? GIE_VOX_OCCUPIED : GIE_VOX_FREE;
 }
 
-// updateHashOGMWithPntCld / updateHashOGMWithSensor.  Each thread owns VEC consecutive voxels along x (vector loads /
-// stores on the dense arrays); a grid-stride loop over a grid sized to the SM count keeps CTAs resident.
+// updateHashOGMWithPntCld / updateHashOGMWithSensor (unify_helper.cuh:35-197) + allocHashTB (glb_hash_map.cu:58-113).
+//
+// Block-centric: the sensor kernels flag the blocks they wrote into (HashDev::touched), and the merge visits the blocks that
+// are touched or allocated and intersect the local volume — a few percent of the table in the headline scene — one block
+// per CTA pass: counters are read and reset only inside touched blocks, a touched block with an observed voxel is
+// allocated on the spot (before any of its voxels is merged, like the reference's allocate-everything-first order), hash
+// pools are accessed as 512 consecutive entries per field, and glb_type (cleared to UNKNOWN for the whole volume by a
+// memset) is written for the voxels of allocated blocks.
 // external obstacles (unify_helper.cuh:68-86,149-162; insideAABB voxmap_utils.cuh:203-207): box 0 is a fence (obstacle
 // when OUTSIDE it), boxes 1.. are obstacles inside.  obs[i] = {ll.xyz, ur.xyz, activated}
 __device__ __forceinline__ bool ext_obs_flag(const LocDev &m, int3 glb, int n_obs, const float *__restrict__ obs)
@@ -85,149 +91,95 @@ __device__ __forceinline__ bool ext_obs_flag(const LocDev &m, int3 glb, int n_ob
     return false;
 }
 
-template <bool PNTCLD, int VEC>
-__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
-                                                   int tpr_log2)
+__global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int *__restrict__ count)
 {
-    // A CTA pass covers 256 >> tpr_log2 rows (y,z) of the volume with 1 << tpr_log2 threads per row; everything that
-    // depends only on (y,z) — the block-table row, the voxel offset inside a block — is computed once per row, and all loop
-    // bounds are uniform so that the rare allocation path can use warp collectives.
-    const int gx = m.X / VEC;                        // X % VEC == 0: a group of VEC voxels never straddles a row
-    const int tpr = 1 << tpr_log2, rpc = 256 >> tpr_log2;
-    const int r_in = threadIdx.x >> tpr_log2, xg0 = threadIdx.x & (tpr - 1);
-    const int nrows = m.Y * m.Z;
     const int lane = threadIdx.x & 31;
-    for (int row0 = blockIdx.x * rpc; row0 < nrows; row0 += gridDim.x * rpc) {
-        const int row = row0 + r_in;
-        const bool row_ok = row < nrows;
-        const int y = row_ok ? row % m.Y : 0, z = row_ok ? row / m.Y : 0;
-        const int gy = y + m.pvt.y, gz = z + m.pvt.z;
-        const int trow = (((gz >> 3) - h.tab_org.z) * h.tab_dim.y + ((gy >> 3) - h.tab_org.y)) * h.tab_dim.x - h.tab_org.x;
-        const int vrow = (gz & 7) * 64 + (gy & 7) * 8;
-        for (int xgb = 0; xgb < gx; xgb += tpr) {
-            const int xg = xgb + xg0;
-            const bool valid = row_ok && xg < gx;
-            const int x0 = xg * VEC;
-            const int id0 = valid ? row * m.X + x0 : 0;
-            const int gx0 = x0 + m.pvt.x;
-            int cnt[VEC], ti[VEC], blk[VEC];
-            int8_t inst[VEC], out_type[VEC];
-            if (VEC >= 4) {   // VEC consecutive voxels per thread: 16-byte loads of the counters, all issued before any use
-#pragma unroll
-                for (int v = 0; v < VEC; v += 4) {
-                    char4 i4 = valid ? *reinterpret_cast<const char4 *>(m.inst_type + id0 + v) : make_char4(0, 0, 0, 0);
-                    inst[v] = i4.x; inst[v + 1] = i4.y; inst[v + 2] = i4.z; inst[v + 3] = i4.w;
-                    int4 c4 = make_int4(0, 0, 0, 0);
-                    if (PNTCLD && valid) c4 = *reinterpret_cast<const int4 *>(m.ray_count + id0 + v);
-                    cnt[v] = c4.x; cnt[v + 1] = c4.y; cnt[v + 2] = c4.z; cnt[v + 3] = c4.w;
-                }
-            } else {
-                inst[0] = valid ? m.inst_type[id0] : 0;
-                cnt[0] = (PNTCLD && valid) ? m.ray_count[id0] : 0;
-            }
-            bool any_cnt = false, any_inst = false, any_need = false, any_blk = false;
-            bool observed[VEC];
-#pragma unroll
-            for (int k = 0; k < VEC; k++) {
-                any_cnt |= cnt[k] != 0; any_inst |= inst[k] != GIE_VOX_UNKNOWN;
-                observed[k] = valid && (PNTCLD ? (cnt[k] != 0) : (inst[k] == GIE_VOX_OCCUPIED || inst[k] == GIE_VOX_FREE));
-                ti[k] = trow + ((gx0 + k) >> 3);
-                if (k > 0 && ti[k] == ti[k - 1]) blk[k] = blk[k - 1];
-                else blk[k] = valid ? __ldcg(&h.btab[ti[k]]) : -1;
-                any_need |= observed[k] && blk[k] < 0;
-                any_blk |= blk[k] >= 0;
-            }
-            if (__any_sync(0xffffffffu, any_need)) {
-                // rare after the first frames.  Warp-aggregated allocation: one lane per distinct missing block inserts,
-                // the others take its result
-#pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    bool need = observed[k] && blk[k] < 0;
-                    if (need) {   // a sibling voxel of this thread (or another warp) may have created the block meanwhile
-                        int b = __ldcg(&h.btab[ti[k]]);
-                        if (b >= 0) { blk[k] = b; need = false; }
-                    }
-                    unsigned grp = __match_any_sync(0xffffffffu, need ? ti[k] : -1);
-                    int leader = __ffs(grp) - 1;
-                    int res = -1;
-                    if (need && lane == leader) {
-                        res = hash_insert(h, make_int3((gx0 + k) >> 3, gy >> 3, gz >> 3));
-                        if (res >= 0) h.btab[ti[k]] = res;
-                    }
-                    res = __shfl_sync(0xffffffffu, res, leader);
-                    if (need) blk[k] = res;
-                    any_blk |= blk[k] >= 0;
-                }
-            }
-            if (!valid) continue;
-#pragma unroll
-            for (int k = 0; k < VEC; k++) out_type[k] = GIE_VOX_UNKNOWN;
-            if (any_blk) {
-#pragma unroll
-                for (int k = 0; k < VEC; k++) {
-                    if (blk[k] < 0) continue;
-                    const int3 glb = make_int3(gx0 + k, gy, gz);
-                    size_t vi = (size_t)blk[k] * 512 + vrow + (glb.x & 7);
-                    int8_t type = h.vox_type[vi];
-                    const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
-                    if (observed[k] || occ_flag) {
-                        const int8_t old_type = type;
-                        uint8_t occ = h.occ_val[vi];
-                        if (PNTCLD) {
-                            if (cnt[k] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
-                            else {
-                                float p = fminf(1.f, __fdiv_rn((float)(-cnt[k]), 10.f));
-                                set_occ_val(occ, type, 0.f, p, m.thresh);
-                            }
-                        } else {
-                            if (inst[k] == GIE_VOX_OCCUPIED || occ_flag) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
-                            else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
-                        }
-                        h.occ_val[vi] = occ;
-                        h.vox_type[vi] = type;
-                        if (stream && type != old_type) h.dirty[blk[k]] = 1;
-                    }
-                    out_type[k] = type;
-                }
-            }
-            if (VEC >= 4) {
-#pragma unroll
-                for (int v = 0; v < VEC; v += 4) {
-                    if (any_cnt) *reinterpret_cast<int4 *>(m.ray_count + id0 + v) = make_int4(0, 0, 0, 0);
-                    if (any_inst) *reinterpret_cast<char4 *>(m.inst_type + id0 + v) = make_char4(0, 0, 0, 0);
-                    *reinterpret_cast<char4 *>(m.glb_type + id0 + v) = make_char4(out_type[v], out_type[v + 1], out_type[v + 2], out_type[v + 3]);
-                }
-            } else {
-                if (any_cnt) m.ray_count[id0] = 0;
-                if (any_inst) m.inst_type[id0] = GIE_VOX_UNKNOWN;
-                m.glb_type[id0] = out_type[0];
-            }
+    const int padded = (entries + 31) & ~31;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
+        bool take = false;
+        if (i < entries && (__ldcg(&h.btab[i]) >= 0 || h.touched[i])) {
+            int3 k = make_int3(i % h.tab_dim.x, (i / h.tab_dim.x) % h.tab_dim.y, i / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
+            int3 lo = make_int3(k.x * 8, k.y * 8, k.z * 8) - m.pvt;
+            take = lo.x + 7 >= 0 && lo.x < m.X && lo.y + 7 >= 0 && lo.y < m.Y && lo.z + 7 >= 0 && lo.z < m.Z;
         }
+        unsigned bal = __ballot_sync(0xffffffffu, take);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(count, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (take) list[base + __popc(bal & ((1u << lane) - 1))] = i;
     }
 }
 
-// Allocation-only pre-pass, used when external-obstacle boxes are active: the reference allocates every touched block
-// before the merge (allocHashTB), so a box voxel must see a block that another voxel's observation creates this frame.
 template <bool PNTCLD>
-__global__ void __launch_bounds__(256) k_alloc_observed(LocDev m, HashDev h)
+__global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
+                                                   const int *__restrict__ list, const int *__restrict__ count)
 {
-    const int n_pad = (m.N + 31) & ~31;
-    const int lane = threadIdx.x & 31;
-    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < n_pad; id += gridDim.x * blockDim.x) {
-        const bool valid = id < m.N;
-        bool observed = false;
-        int ti = -1;
-        int3 glb = make_int3(0, 0, 0);
-        if (valid) {
-            observed = PNTCLD ? (m.ray_count[id] != 0) : (m.inst_type[id] == GIE_VOX_OCCUPIED || m.inst_type[id] == GIE_VOX_FREE);
-            glb = make_int3(id % m.X, (id / m.X) % m.Y, id / (m.X * m.Y)) + m.pvt;
-            ti = gie_tab_index(h, glb);
+    __shared__ int s_blk;
+    const int n = __ldcg(count);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int ti = __ldcg(&list[b]);
+        const bool touched = h.touched[ti] != 0;
+        int blk = __ldcg(&h.btab[ti]);
+        const int3 k = make_int3(ti % h.tab_dim.x, (ti / h.tab_dim.x) % h.tab_dim.y, ti / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
+        // two voxels per thread (v = tid, tid + 256), engine order inside the block (x fastest)
+        int id[2], cnt[2];
+        int8_t inst[2];
+        bool inside[2], observed[2];
+        bool any_obs = false;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int v = threadIdx.x + 256 * u;
+            const int3 c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - m.pvt;
+            inside[u] = gie_inside_loc(m, c);
+            id[u] = inside[u] ? gie_lidx(m, c) : 0;
+            cnt[u] = 0; inst[u] = GIE_VOX_UNKNOWN;
+            if (inside[u] && touched) {   // reset observation of one scan (unify_helper.cuh:48-51,131-133)
+                inst[u] = m.inst_type[id[u]];
+                if (PNTCLD) cnt[u] = m.ray_count[id[u]];
+                if (inst[u] != GIE_VOX_UNKNOWN) m.inst_type[id[u]] = GIE_VOX_UNKNOWN;
+                if (PNTCLD && cnt[u] != 0) m.ray_count[id[u]] = 0;
+            }
+            observed[u] = PNTCLD ? (cnt[u] != 0) : (inst[u] == GIE_VOX_OCCUPIED || inst[u] == GIE_VOX_FREE);
+            any_obs |= observed[u];
         }
-        const bool need = observed && __ldcg(&h.btab[ti]) < 0;
-        unsigned grp = __match_any_sync(0xffffffffu, need ? ti : -1);
-        if (need && lane == __ffs(grp) - 1) {
-            int res = hash_insert(h, gie_vb_key(glb));
-            if (res >= 0) h.btab[ti] = res;
+        if (blk < 0) {   // uniform across the CTA
+            if (!__syncthreads_or(any_obs)) continue;      // never observed, not allocated: glb_type stays UNKNOWN
+            if (threadIdx.x == 0) {
+                int res = hash_insert(h, k);
+                if (res >= 0) h.btab[ti] = res;
+                s_blk = res;
+            }
+            __syncthreads();
+            blk = s_blk;
+            __syncthreads();
+            if (blk < 0) continue;                         // pool exhausted: status bit is set
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (!inside[u]) continue;
+            const int v = threadIdx.x + 256 * u;
+            const size_t vi = (size_t)blk * 512 + v;
+            int8_t type = h.vox_type[vi];
+            const int3 glb = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6));
+            const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
+            if (observed[u] || occ_flag) {
+                const int8_t old_type = type;
+                uint8_t occ = h.occ_val[vi];
+                if (PNTCLD) {
+                    if (cnt[u] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
+                    else {
+                        float p = fminf(1.f, __fdiv_rn((float)(-cnt[u]), 10.f));
+                        set_occ_val(occ, type, 0.f, p, m.thresh);
+                    }
+                } else {
+                    if (inst[u] == GIE_VOX_OCCUPIED || occ_flag) set_occ_val(occ, type, 250.f, 0.8f, m.thresh);
+                    else set_occ_val(occ, type, 0.f, 0.5f, m.thresh);
+                }
+                h.occ_val[vi] = occ;
+                h.vox_type[vi] = type;
+                if (stream && type != old_type) h.dirty[blk] = 1;
+            }
+            m.glb_type[id[u]] = type;
         }
     }
 }
@@ -300,6 +252,7 @@ int gie_hash_begin_frame(gie_hashmap *hm)
     gie_locmap *lm = hm->lm;
     hm->d.tab_org = gie_vb_key(lm->d.pvt) - make_int3(hm->halo_blocks, hm->halo_blocks, hm->halo_blocks);
     int entries = (int)hm->tab_entries;
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->d.touched, 0, hm->tab_entries, lm->stream));
     k_build_btab<<<(entries + 255) / 256, 256, 0, lm->stream>>>(hm->d, entries);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
@@ -311,30 +264,15 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     const float *obs = hm->obs_dev;
     gie_locmap *lm = hm->lm;
     StageTimer t(lm, GIE_ST_HASH_MERGE);
-    const int vec = (lm->d.X % 8 == 0) ? 8 : (lm->d.X % 4 == 0) ? 4 : 1;
-    const int gx = lm->d.X / vec;
-    int tpr_log2 = 5;
-    while ((1 << tpr_log2) < gx && tpr_log2 < 8) tpr_log2++;
-    const int rpc = 256 >> tpr_log2;
-    const long long passes = ((long long)lm->d.Y * lm->d.Z + rpc - 1) / rpc;
-    int grid = (int)std::min<long long>(passes, (long long)lm->num_sms * 16);
-    if (n_obs > 0) {
-        int g1 = (int)std::min<long long>(((long long)lm->d.N + 255) / 256, (long long)lm->num_sms * 16);
-        if (input_pntcld) k_alloc_observed<true><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
-        else k_alloc_observed<false><<<g1, 256, 0, lm->stream>>>(lm->d, hm->d);
-        lm->launches++;
-    }
-    if (vec == 8) {
-        if (input_pntcld) k_merge_ogm<true, 8><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-        else k_merge_ogm<false, 8><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-    } else if (vec == 4) {
-        if (input_pntcld) k_merge_ogm<true, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-        else k_merge_ogm<false, 4><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-    } else {
-        if (input_pntcld) k_merge_ogm<true, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-        else k_merge_ogm<false, 1><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, tpr_log2);
-    }
-    lm->launches++;
+    const int entries = (int)hm->tab_entries;
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->merge_count, 0, sizeof(int), lm->stream));
+    GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));   // UNKNOWN wherever no block exists
+    k_list_merge_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, hm->merge_list,
+                                                                                           hm->merge_count);
+    const int grid = lm->num_sms * 16;
+    if (input_pntcld) k_merge_ogm<true><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, hm->merge_list, hm->merge_count);
+    else k_merge_ogm<false><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, hm->merge_list, hm->merge_count);
+    lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

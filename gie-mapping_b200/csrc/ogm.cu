@@ -36,7 +36,7 @@ __device__ __forceinline__ float3 coord2pos(const LocDev &m, int3 c)
 }
 
 // registerLocObs (pntcld_raycast.cu:83-102)
-__global__ void k_pc_register(LocDev m, const float *__restrict__ pts, int n)
+__global__ void k_pc_register(LocDev m, HashDev h, const float *__restrict__ pts, int n)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -48,6 +48,7 @@ __global__ void k_pc_register(LocDev m, const float *__restrict__ pts, int n)
             int id = gie_lidx(m, loc);
             m.inst_type[id] = GIE_VOX_OCCUPIED;
             atomicAdd(&m.ray_count[id], 1);
+            gie_touch_block(h, loc + m.pvt);
         }
     }
 }
@@ -59,7 +60,7 @@ __global__ void k_pc_register(LocDev m, const float *__restrict__ pts, int n)
 // WIN^3 window around the origin voxel in shared memory and flushes the window once at the end (sums commute, the result
 // is identical); decrements outside the window go straight to global memory.
 constexpr int RAY_WIN = 16;
-__global__ void __launch_bounds__(128) k_pc_free(LocDev m, const float *__restrict__ pts, int n, float max_length)
+__global__ void __launch_bounds__(128) k_pc_free(LocDev m, HashDev h, const float *__restrict__ pts, int n, float max_length)
 {
     __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
     for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) win[k] = 0;
@@ -68,7 +69,10 @@ __global__ void __launch_bounds__(128) k_pc_free(LocDev m, const float *__restri
     const int3 p0i = pos2coord(m, p0);
     const int3 worg = p0i - make_int3(RAY_WIN / 2, RAY_WIN / 2, RAY_WIN / 2);   // global coords of window cell (0,0,0)
     // decrement of an in-volume voxel given its GLOBAL coords
+    int last_ti = -1;
     auto dec = [&](int3 g, int id) {
+        int ti = gie_tab_index(h, g);
+        if (ti != last_ti) { h.touched[ti] = 1; last_ti = ti; }
         int3 q = g - worg;
         if ((unsigned)q.x < RAY_WIN && (unsigned)q.y < RAY_WIN && (unsigned)q.z < RAY_WIN) atomicAdd(&win[(q.z * RAY_WIN + q.y) * RAY_WIN + q.x], -1);
         else atomicAdd(&m.ray_count[id], -1);   // result unused -> RED
@@ -150,7 +154,7 @@ __global__ void __launch_bounds__(128) k_pc_free(LocDev m, const float *__restri
 }
 
 // robot sphere of getAllocKeys (pntcld_raycast.cu:33-41): count = -1 inside the sphere, after the ray casting
-__global__ void k_pc_sphere(LocDev m, int r2, int r)
+__global__ void k_pc_sphere(LocDev m, HashDev h, int r2, int r)
 {
     int side = 2 * r + 1;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -158,7 +162,7 @@ __global__ void k_pc_sphere(LocDev m, int r2, int r)
     int3 d = make_int3(i % side - r, (i / side) % side - r, i / (side * side) - r);
     if (d.x * d.x + d.y * d.y + d.z * d.z > r2) return;
     int3 c = d + m.half;
-    if (gie_inside_loc(m, c)) m.ray_count[gie_lidx(m, c)] = -1;
+    if (gie_inside_loc(m, c)) { m.ray_count[gie_lidx(m, c)] = -1; gie_touch_block(h, c + m.pvt); }
 }
 
 __device__ __forceinline__ int pos_mod(int i, int n) { return (i % n + n) % n; }
@@ -179,14 +183,14 @@ struct SensorParam {
 
 // setLocalOccupancy of the three projective sensors; one thread per voxel, x fastest
 template <int SENSOR>
-__global__ void __launch_bounds__(256) k_projective(LocDev m, const float *__restrict__ data, SensorParam sp, int fmp, int r2)
+__global__ void __launch_bounds__(256) k_projective(LocDev m, HashDev h, const float *__restrict__ data, SensorParam sp, int fmp, int r2)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, z = blockIdx.z;
     if (x >= m.X) return;
     int3 c = make_int3(x, y, z);
     int id = gie_lidx(m, c);
-    if (fmp && robot_sphere(m, c, r2)) { m.inst_type[id] = GIE_VOX_FREE; return; }
+    if (fmp && robot_sphere(m, c, r2)) { m.inst_type[id] = GIE_VOX_FREE; gie_touch_block(h, c + m.pvt); return; }
     float3 gp = coord2pos(m, c + m.pvt);
     float3 l = se3_apply(m.G2L, gp);
     int8_t out = GIE_VOX_UNKNOWN;
@@ -230,16 +234,16 @@ __global__ void __launch_bounds__(256) k_projective(LocDev m, const float *__res
         else if (depth > real + m.w) out = GIE_VOX_UNKNOWN;
         else if (gp.z >= m.min_h && gp.z <= m.max_h) out = GIE_VOX_OCCUPIED;
     }
-    if (out != GIE_VOX_UNKNOWN) m.inst_type[id] = out;
+    if (out != GIE_VOX_UNKNOWN) { m.inst_type[id] = out; gie_touch_block(h, c + m.pvt); }
 }
 
 template <int SENSOR>
-int launch_projective(gie_locmap *lm, const float *data, const SensorParam &sp, int fmp, int r2)
+int launch_projective(gie_locmap *lm, gie_hashmap *hm, const float *data, const SensorParam &sp, int fmp, int r2)
 {
     StageTimer t(lm, GIE_ST_OGM);
     dim3 block(256), grid((lm->d.X + 255) / 256, lm->d.Y, lm->d.Z);
     if (lm->d.X <= 128) { block = dim3(128); grid.x = (lm->d.X + 127) / 128; }
-    k_projective<SENSOR><<<grid, block, 0, lm->stream>>>(lm->d, data, sp, fmp, r2);
+    k_projective<SENSOR><<<grid, block, 0, lm->stream>>>(lm->d, hm->d, data, sp, fmp, r2);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -304,45 +308,45 @@ int gie_launch_pc_repack(gie_locmap *lm, const unsigned char *raw_dev, int n, in
     return GIE_OK;
 }
 
-int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *, const float *pts_dev, int n, int fmp, int r2)
+int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_dev, int n, int fmp, int r2)
 {
     StageTimer t(lm, GIE_ST_OGM);
     if (n > 0) {
         int blocks = (n + 255) / 256;
-        k_pc_register<<<blocks, 256, 0, lm->stream>>>(lm->d, pts_dev, n);
+        k_pc_register<<<blocks, 256, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n);
         // pntcld_raycast.cu:79: 0.707f*loc_map._local_size.x*loc_map._voxel_width
         float max_len = 0.707f * (float)lm->d.X * lm->d.w;
-        k_pc_free<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, pts_dev, n, max_len);
+        k_pc_free<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len);
         lm->launches += 2;
     }
     if (fmp) {
         int r = 0;
         while (r * r <= r2) r++;
         int side = 2 * r + 1, tot = side * side * side;
-        k_pc_sphere<<<(tot + 255) / 256, 256, 0, lm->stream>>>(lm->d, r2, r);
+        k_pc_sphere<<<(tot + 255) / 256, 256, 0, lm->stream>>>(lm->d, hm->d, r2, r);
         lm->launches++;
     }
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
 
-int gie_launch_ogm_scan2d(gie_locmap *lm, gie_hashmap *, const float *scan, int scan_num, float tinc, float tmin, int fmp, int r2)
+int gie_launch_ogm_scan2d(gie_locmap *lm, gie_hashmap *hm, const float *scan, int scan_num, float tinc, float tmin, int fmp, int r2)
 {
     SensorParam sp{};
     sp.scan_num = scan_num; sp.theta_inc = tinc; sp.theta_min = tmin;
-    return launch_projective<SENSOR_SCAN2D>(lm, scan, sp, fmp, r2);
+    return launch_projective<SENSOR_SCAN2D>(lm, hm, scan, sp, fmp, r2);
 }
-int gie_launch_ogm_vlp16(gie_locmap *lm, gie_hashmap *, const float *ranges, int scan_num, int ring_num, float tinc,
+int gie_launch_ogm_vlp16(gie_locmap *lm, gie_hashmap *hm, const float *ranges, int scan_num, int ring_num, float tinc,
                          float tmin, float pinc, float pmin, int fmp, int r2)
 {
     SensorParam sp{};
     sp.scan_num = scan_num; sp.ring_num = ring_num; sp.theta_inc = tinc; sp.theta_min = tmin; sp.phi_inc = pinc; sp.phi_min = pmin;
-    return launch_projective<SENSOR_VLP16>(lm, ranges, sp, fmp, r2);
+    return launch_projective<SENSOR_VLP16>(lm, hm, ranges, sp, fmp, r2);
 }
-int gie_launch_ogm_depth(gie_locmap *lm, gie_hashmap *, const float *img, int rows, int cols, float cx, float cy,
+int gie_launch_ogm_depth(gie_locmap *lm, gie_hashmap *hm, const float *img, int rows, int cols, float cx, float cy,
                          float fx, float fy, int valid_nan, int fmp, int r2)
 {
     SensorParam sp{};
     sp.rows = rows; sp.cols = cols; sp.cx = cx; sp.cy = cy; sp.fx = fx; sp.fy = fy; sp.valid_nan = valid_nan;
-    return launch_projective<SENSOR_DEPTH>(lm, img, sp, fmp, r2);
+    return launch_projective<SENSOR_DEPTH>(lm, hm, img, sp, fmp, r2);
 }
