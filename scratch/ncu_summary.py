@@ -8,7 +8,7 @@ def col(name): return hdr.index(name)
 def val(r, name):
     i = col(name)
     return float(r[i].replace(",", "")) * SC.get(units[i], 1.0)
-names = ['k_build_btab', 'k_pc_register', 'k_pc_free', 'k_merge_ogm', 'k_alloc_observed', 'k_edt_ybits', 'k_edt_ycols', 'k_edt_slices', 'k_edt_xsweep',
+names = ['k_list_merge_blocks', 'k_build_btab', 'k_pc_register', 'k_pc_free', 'k_merge_ogm', 'k_alloc_observed', 'k_edt_ybits', 'k_edt_ycols', 'k_edt_slices', 'k_edt_xsweep',
          'k_edt_zsweep', 'k_list_blocks', 'k_mark_blocks', 'k_mark', 'k_frontiers', 'k_waves', 'k_commit', 'k_wave_stats']
 per = {}
 keep = ['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
@@ -22,7 +22,7 @@ with open(out_csv, "w") as f:
         t, rd, wr = val(r, 'gpu__time_duration.sum'), val(r, 'dram__bytes_read.sum'), val(r, 'dram__bytes_write.sum')
         per[short] = {"us": t, "dram_bytes": rd + wr}
         w.writerow([short, r[col('Grid Size')], r[col('Block Size')], f"{t:.2f}", int(rd), int(wr)] + [r[col(k)] for k in keep])
-grp = {"batch_dt": ["k_edt_ybits", "k_edt_ycols", "k_edt_slices", "k_edt_xsweep", "k_edt_zsweep"], "hash_merge": ["k_build_btab", "k_merge_ogm"],
+grp = {"batch_dt": ["k_edt_ybits", "k_edt_ycols", "k_edt_slices", "k_edt_xsweep", "k_edt_zsweep"], "hash_merge": ["k_build_btab", "k_list_merge_blocks", "k_merge_ogm"],
        "mark_frontier": ["k_list_blocks", "k_mark", "k_mark_blocks", "k_frontiers"], "commit": ["k_commit"]}
 out = {g: sum(per[n]["dram_bytes"] for n in ns if n in per) for g, ns in grp.items()}
 out["_source"] = label
