@@ -160,6 +160,28 @@ def batch_dt_dense_case(gie, cfg, stream):
     return {"workload": f"{X}x{Y}x{Z}, random 0.2 % occupancy in every slice", "ms": ms, "achieved": ach, "frac": ach / peak}
 
 
+def cpp_host_leg(gie, cfg, frames, warmup):
+    """The same frames through the C++ host surface (include/gie_compat: LocMap / GlbHashMap / localOGMKernels /
+    batchEDTUpdate / mergeNewObsv, driven by gie-mapping_b200/gie_replay) with pageable host buffers and blocking copies, timed
+    per frame on the host with a device synchronise at both ends — the way the reference times itself
+    (volumetric_mapper.cpp:152-203) and the way `--impl reference` is timed."""
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            _, _, out = gie.replay_io.run_replay(cfg, frames, d, timing=True)
+        t = []
+        for line in out.splitlines():
+            if line.startswith("frame "):
+                p = line.split()
+                t.append(float(p[3]) + float(p[5]))
+        t = t[warmup:]
+        ms = float(np.mean(t))
+        return {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_step": ms, "frames": len(t),
+                "how": "gie_replay --time: C++ host, pageable buffers, cudaMemcpy + cudaDeviceSynchronize per half frame"}
+    except Exception as e:
+        return {"error": repr(e)[:300]}
+
+
 def sharded_edt_leg(world, rank):
     """BASELINE configs[4] shape (1024^3-class volume sharded over the GPUs of the box): the batch EDT with its z-slab <->
     y-slab NCCL all-to-all (gie-mapping_b200/sharded.py).  Extra information, not part of `value`: the per-frame pipeline
@@ -379,6 +401,8 @@ def main():
             "roofline": roofline, "clocks": clocks}
     if not args.no_sharded_edt and (world > 1 or args.sharded_edt):
         line["sharded_batch_edt"] = sharded_edt_leg(world, rank)
+    if rank == 0 and world == 1:
+        line["e2e_cpp_host"] = cpp_host_leg(gie, cfg, frames, args.warmup)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(gie, cfg, frames)

@@ -878,8 +878,10 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         const int entries = (int)hm->tab_entries;
         k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(m, hm->d, entries, hm->blk_list, hm->blk_count);
         const int *n_slices = lm->edt_meta + 2 * m.Z;
-        if (vec == 4) k_mark<4><<<grid, 256, 0, lm->stream>>>(m, hm->d, n_slices);
-        else k_mark<1><<<grid, 256, 0, lm->stream>>>(m, hm->d, n_slices);
+        // (grid-stride kernel that returns at once unless the volume holds no obstacle: a small grid keeps the launch cheap)
+        const int grid_mark = std::min(grid, lm->num_sms * 4);
+        if (vec == 4) k_mark<4><<<grid_mark, 256, 0, lm->stream>>>(m, hm->d, n_slices);
+        else k_mark<1><<<grid_mark, 256, 0, lm->stream>>>(m, hm->d, n_slices);
         k_mark_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, n_slices, hm->blk_list, hm->blk_count);
         k_frontiers<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
     }

@@ -67,9 +67,12 @@ def run_replay(cfg, frames, workdir, stream=False, costmap=False, timing=False):
         raise RuntimeError(f"{exe} is missing: build it with `make -C gie-mapping_b200/host`")
     inp, outp = os.path.join(workdir, "frames.bin"), os.path.join(workdir, "out.bin")
     write_frames(inp, cfg, frames)
-    cmd = [exe, inp, outp] + (["--stream"] if stream else []) + (["--costmap"] if costmap else []) + (["--time"] if timing else [])
+    # timing runs dump nothing (the per-frame arrays of a 512^3 volume are 2.8 GB)
+    cmd = [exe, inp, "-" if timing else outp] + (["--stream"] if stream else []) + (["--costmap"] if costmap else []) + (["--time"] if timing else [])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"gie_replay failed ({res.returncode}): {res.stdout[-1000:]} {res.stderr[-2000:]}")
+    if timing:
+        return None, None, res.stdout
     out, mirror = read_output(outp, cfg, len(frames), stream, costmap)
     return out, mirror, res.stdout
