@@ -34,7 +34,9 @@ struct LocalQ {
     int n[2];
     int total, nmax;
     int spill_base;
+    int solo_level, solo_cb;
 };
+constexpr int SOLO_ENTER = 256;   // frontier size at or below which ONE CTA runs the levels alone (6 * 256 pushes fit LQ_CAP)
 
 // Wave-C queue entry.  low word: local voxel coords packed 10/10/10 (X, Y <= 1024, Z <= 1022), so that no kernel has to
 // divide a linear index back into coordinates; high word: the coc id the PUSHER offered.  De-duplication is by that id:
@@ -68,6 +70,7 @@ struct WaveDev {
     uint32_t *snap_id;
     int display;   // display_glb_edt: record changed blocks for streaming
     int cluster_size, local_enter, local_spill;   // cluster-local mode of wave C
+    int no_solo; // GIE_WAVE_NO_SOLO: keep the tail of wave C in the cluster mode (measurement switch)
     int epoch;   // value that marks a voxel as "already a wave-C seed" in m.wave_layer for THIS merge (never reused, so the
                  // array needs no per-frame clearing; the reference rewrites _loc_wave_layer for every voxel)
 
@@ -558,6 +561,64 @@ __device__ void waveC_phase2(const LocDev &m, const HashDev &h, const WaveDev &w
     }
 }
 
+// The tail of wave C: with a frontier of at most SOLO_ENTER voxels even the cluster barriers (2 x ~0.5 us per level) dominate,
+// so CTA 0 of the cluster takes the whole frontier and runs the levels alone with __syncthreads and shared-memory queue
+// atomics, until the frontier is empty or has grown again.  Same relaxation, same de-duplication.  cb = buffer holding the
+// frontier of `level`, on entry and on return.
+__device__ int wave_c_solo(const LocDev &m, const HashDev &h, const WaveDev &w, LocalQ &lq, int level, int &cb)
+{
+    const int t = threadIdx.x, T = blockDim.x, lane = t & 31;
+    for (;;) {
+        const int n = min(lq.n[cb], LQ_CAP);
+        const bool tr = w.trace && t == 0 && level < TRACE_LEVELS;
+        if (tr) { w.trace[level * 6] = 2000000000ULL + n; w.trace[level * 6 + 1] = gtimer(); }
+        for (int k = t; k < n; k += T) {
+            unsigned long long e = lq.q[cb][k];
+            uint32_t want = (uint32_t)(e >> 32);
+            uint32_t sid = gie_pair_id(__ldcg(&m.pair[gie_lidx(m, c_entry_coord(e))]));
+            lq.snap[k] = (want == C_ALWAYS || want == sid) ? sid : 0xffffffffu;
+        }
+        if (t == 0) lq.n[cb ^ 1] = 0;
+        __syncthreads();
+        for (int k0 = t - lane; k0 < n; k0 += T) {   // warp-uniform trip count
+            const int k = k0 + lane;
+            uint32_t sid = k < n ? lq.snap[k] : 0xffffffffu;
+            CRelax rx;
+#pragma unroll
+            for (int d = 0; d < 6; d++) { rx.in[d] = false; rx.key[d] = 0; rx.old[d] = 0; rx.nb[d] = make_int3(0, 0, 0); }
+            if (sid != 0xffffffffu) c_relax(m, c_entry_coord(lq.q[cb][k]), sid, rx);
+            int mine = 0;
+#pragma unroll
+            for (int d = 0; d < 6; d++) { rx.in[d] = rx.in[d] && rx.key[d] < rx.old[d]; mine += rx.in[d]; }
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&lq.n[cb ^ 1], total);
+                base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+                for (int d = 0; d < 6; d++) {
+                    if (!rx.in[d]) continue;
+                    if (base < LQ_CAP) lq.q[cb ^ 1][base] = c_entry(rx.nb[d], sid);
+                    else atomicOr(h.status, GIE_DEV_ERR_QUEUE_OVERFLOW);   // cannot happen: at most 6 * SOLO_ENTER pushes
+                    base++;
+                }
+            }
+        }
+        __syncthreads();
+        if (tr) w.trace[level * 6 + 5] = gtimer();
+        level++; cb ^= 1;
+        const int nn = lq.n[cb];
+        if (nn == 0 || nn > SOLO_ENTER) break;
+    }
+    return level;
+}
+
 // Wave C while the frontier is small (the common case: a few hundred to a few thousand voxels per level for hundreds of
 // levels).  A grid-wide level costs two grid barriers plus global-queue round trips (~11 us measured); here ONE thread-block
 // cluster runs the levels on its own: every CTA keeps its share of the frontier in shared memory, pushes go to a peer CTA's
@@ -657,9 +718,32 @@ __device__ int wave_c_local(const LocDev &m, const HashDev &h, const WaveDev &w,
         }
         __syncthreads();
         if (tr) w.trace[(level - 1) * 6 + 5] = gtimer();
-        const int total = lq.total;
+        int total = lq.total, nmax = lq.nmax;
+        if (total > 0 && total <= SOLO_ENTER && nmax <= LQ_CAP && !w.no_solo) {
+            // hand the whole frontier to CTA 0 and let it run alone (wave_c_solo); the other CTAs park at the cluster barrier
+            if (r != 0) {
+                const int mine = lq.n[cb];
+                if (t == 0) lq.spill_base = mine ? atomicAdd(cl.map_shared_rank(&lq.n[cb], 0), mine) : 0;
+                __syncthreads();
+                unsigned long long *q0 = cl.map_shared_rank(&lq.q[cb][0], 0);
+                for (int k = t; k < mine; k += T) q0[lq.spill_base + k] = lq.q[cb][k];
+                __syncthreads();
+                if (t == 0) { lq.n[0] = 0; lq.n[1] = 0; }
+            }
+            cl.sync();
+            if (r == 0) {
+                level = wave_c_solo(m, h, w, lq, level, cb);
+                if (t == 0) { lq.solo_level = level; lq.solo_cb = cb; }
+            }
+            cl.sync();
+            level = *cl.map_shared_rank(&lq.solo_level, 0);
+            cb = *cl.map_shared_rank(&lq.solo_cb, 0);
+            total = *cl.map_shared_rank(&lq.n[cb], 0);
+            nmax = total;
+            cl.sync();   // everyone has read CTA 0's result before it is overwritten
+        }
         if (total == 0) break;
-        if (lq.nmax > LQ_CAP || total > spill_at) {
+        if (nmax > LQ_CAP || total > spill_at) {
             // hand the frontier to the grid-wide mode: append the local queues to the global queue of this level
             const int mine = min(lq.n[cb], LQ_CAP);
             if (t == 0) lq.spill_base = atomicAdd(&w.cnt[C_C0 + level % 3], mine);
@@ -797,6 +881,7 @@ WaveDev make_wave_dev(gie_hashmap *hm)
     w.local_enter = hm->wave_cluster * LQ_CAP / 4;
     w.local_spill = hm->wave_cluster * LQ_CAP / 2;
     if (getenv("GIE_WAVE_NO_LOCAL")) w.local_enter = 0;
+    w.no_solo = getenv("GIE_WAVE_NO_SOLO") ? 1 : 0;
 
     return w;
 }
