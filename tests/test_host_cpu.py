@@ -156,3 +156,17 @@ def test_oracle_ext_obstacles_and_stream_flags(gie, oracle):
     om.publishMap(f1)
     assert int((om.glb_type == 2).sum()) > occ0
     om.close()
+
+
+def test_compat_host_logic_cpp(tmp_path):
+    """C++ unit checks of the host side of include/gie_compat (coordinate algebra, block addressing, obstacle boxes, cuTT
+    handles, parameter PODs, pose -> projection): compiled with g++, linked against the C ABI library, no GPU call."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "gie-mapping_b200", "csrc")])
+    exe = str(tmp_path / "test_compat_host")
+    libdir = os.path.join(ROOT, "gie-mapping_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", f"-I{ROOT}/include/gie_compat", f"-I{ROOT}/include", "-I/usr/local/cuda/include",
+                           os.path.join(ROOT, "tests", "cpp", "test_compat_host.cpp"), "-o", exe, f"-L{libdir}", "-lgie_b200",
+                           "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "compat host checks OK" in res.stdout
