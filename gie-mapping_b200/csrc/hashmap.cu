@@ -12,6 +12,7 @@
 // missing (a fresh block is all-UNKNOWN, so voxels of that block merged earlier with "no block" are already right).
 #include "engine.h"
 #include <algorithm>
+#include <cuda/barrier>
 
 namespace {
 
@@ -114,7 +115,14 @@ template <bool PNTCLD>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
                                                    const int *__restrict__ list, const int *__restrict__ count)
 {
+    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
     __shared__ int s_blk;
+    __shared__ alignas(16) int8_t s_type[512];
+    __shared__ alignas(16) uint8_t s_occ[512];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+    __shared__ barrier_t bar;
+    if (threadIdx.x == 0) { init(&bar, blockDim.x); cuda::device::experimental::fence_proxy_async_shared_cta(); }
+    __syncthreads();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
@@ -154,17 +162,27 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
             __syncthreads();
             if (blk < 0) continue;                         // pool exhausted: status bit is set
         }
+        // the block's type and occupancy bytes (2 x 512 B, contiguous in the field-major pools) staged by TMA bulk copies
+        {
+            barrier_t::arrival_token tok;
+            if (threadIdx.x == 0) {
+                cuda::device::memcpy_async_tx(s_type, h.vox_type + (size_t)blk * 512, cuda::aligned_size_t<16>(512), bar);
+                cuda::device::memcpy_async_tx(s_occ, h.occ_val + (size_t)blk * 512, cuda::aligned_size_t<16>(512), bar);
+                tok = cuda::device::barrier_arrive_tx(bar, 1, 1024);
+            } else tok = bar.arrive();
+            bar.wait(std::move(tok));
+        }
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             if (!inside[u]) continue;
             const int v = threadIdx.x + 256 * u;
             const size_t vi = (size_t)blk * 512 + v;
-            int8_t type = h.vox_type[vi];
+            int8_t type = s_type[v];
             const int3 glb = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6));
             const bool occ_flag = n_obs > 0 && ext_obs_flag(m, glb, n_obs, obs);
             if (observed[u] || occ_flag) {
                 const int8_t old_type = type;
-                uint8_t occ = h.occ_val[vi];
+                uint8_t occ = s_occ[v];
                 if (PNTCLD) {
                     if (cnt[u] > 0 || occ_flag) set_occ_val(occ, type, 250.f, 1.f, m.thresh);
                     else {
@@ -181,6 +199,7 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
             }
             m.glb_type[id[u]] = type;
         }
+        __syncthreads();   // the staging buffers are free for the next block
     }
 }
 
