@@ -392,20 +392,34 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         // backward (local_edt_core.h:169-192).  Besides _aux / _coc_idx_aux the sweep also writes the (dist, wave-range coc
         // id) pair every voxel starts the merge with (the UNKNOWN-voxel half of MarkLimitedObserve, unify_helper.cuh:201-273),
         // which saves a 17 B/voxel pass over the volume; k_mark then only patches known voxels.
+        // Everything except the distance is constant along one envelope segment (one owner slice), so it is recomputed only when
+        // the owner changes; a z step is then d*d + h, three streaming stores and pointer bumps.
         int c = __ldg(&cxy[base + (size_t)top.s * slice]);
+        int coc_word = 0;
+        uint32_t pid = 0;
+        bool wr_ok = false;
+        auto owner_changed = [&]() {
+            coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+            int3 wr = make_int3((c & 0xffff) + wr0.x, (c >> 16) + wr0.y, top.s + wr0.z);
+            wr_ok = gie_inside_wr(wr);
+            pid = wr_ok ? gie_wr2id(wr) : GIE_INVALID_ID_STALE;
+        };
+        owner_changed();
+        int32_t *pa = m.aux + base + (size_t)(Z - 1) * slice;
+        int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
+        unsigned long long *pp = m.pair + base + (size_t)(Z - 1) * slice;
         for (int u = Z - 1; u >= 0; u--) {
-            int d = u - top.s;
             if (valid) {
-                size_t o = base + (size_t)u * slice;
+                const int d = u - top.s;
                 const int dist = d * d + top.h;
-                __stcs(&m.aux[o], dist);
-                __stcs(&m.coc_aux[o], (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22));
-                int3 wr = make_int3((c & 0xffff) + wr0.x, (c >> 16) + wr0.y, top.s + wr0.z);
-                __stcs(&m.pair[o], gie_inside_wr(wr) ? gie_mk_pair(dist, gie_wr2id(wr)) : gie_mk_pair(GIE_EMPTY_VALUE, GIE_INVALID_ID_STALE));
+                __stcs(pa, dist);
+                __stcs(pc, coc_word);
+                __stcs(pp, gie_mk_pair(wr_ok ? dist : GIE_EMPTY_VALUE, pid));
             }
+            pa -= slice; pc -= slice; pp -= slice;
             if (u == top.t) {
                 q--;
-                if (q >= 0) { top = st.get(q); c = __ldg(&cxy[base + (size_t)top.s * slice]); }
+                if (q >= 0) { top = st.get(q); c = __ldg(&cxy[base + (size_t)top.s * slice]); owner_changed(); }
             }
         }
     }
