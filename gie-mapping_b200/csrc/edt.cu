@@ -354,19 +354,31 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     const size_t slice = (size_t)X * m.Y;
     const int ns = __ldg(n_slices);
     const int3 wr0 = m.pvt - m.upvt;   // local coords -> wave-range coords
+    // A CTA takes WARPS_PER_CTA adjacent 32-wide x groups of one row y at a time and its warps walk z in lockstep (one
+    // __syncthreads per z step), so that every step the CTA writes ONE contiguous run per output array (1 KB / 1 KB / 2 KB at
+    // 8 warps) instead of eight unrelated 128-byte lines at eight different depths: the sweep is bound by its 16 B/voxel of
+    // writes and DRAM page locality decides how fast those go.
+    __shared__ int s_item;
+    const int XG8 = (XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
         if (item >= n_items) break;
-        const int y = item / XG, x = (item - y * XG) * 32 + lane;
-        const bool valid = x < X;
+        const int y = item / XG8, xg = (item - y * XG8) * WARPS_PER_CTA + wid;
+        const int x = xg * 32 + lane;
+        const bool valid = xg < XG && x < X;
         const size_t base = (size_t)y * X + (valid ? x : 0);
         if (ns == 0) {   // no obstacle anywhere: every voxel "sees nothing" (D5)
             for (int u = 0; u < Z && valid; u++) {
                 m.aux[base + (size_t)u * slice] = S * S;
                 m.coc_aux[base + (size_t)u * slice] = x | (INV_Y << 11) | (u << 22);
             }
+            continue;
+        }
+        if (xg >= XG) {   // ragged last group of the row: keep the barrier count of the lockstep loop below
+            for (int u = Z - 1; u >= 0; u--) __syncthreads();
             continue;
         }
         int q = -1;
@@ -409,6 +421,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
         unsigned long long *pp = m.pair + base + (size_t)(Z - 1) * slice;
         for (int u = Z - 1; u >= 0; u--) {
+            __syncthreads();
             if (valid) {
                 const int d = u - top.s;
                 const int dist = d * d + top.h;
@@ -489,7 +502,7 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
     k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
-                                                                      lm->work_counters + 1, m.Y * XG, XG);
+                                                                      lm->work_counters + 1, m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG);
     lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -517,7 +530,7 @@ int gie_launch_batch_edt(gie_locmap *lm)
         StageTimer t(lm, GIE_ST_EDT_Z);
         k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices,
                                                                           (uint2 *)lm->stack_scratch, L, lm->work_counters + 1,
-                                                                          m.Y * XG, XG);
+                                                                          m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG);
     }
     lm->launches += 5;
     GIE_CUDA_CHECK(cudaGetLastError());
