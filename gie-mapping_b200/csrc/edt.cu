@@ -358,7 +358,10 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     // __syncthreads per z step), so that every step the CTA writes ONE contiguous run per output array (1 KB / 1 KB / 2 KB at
     // 8 warps) instead of eight unrelated 128-byte lines at eight different depths: the sweep is bound by its 16 B/voxel of
     // writes and DRAM page locality decides how fast those go.
+    // Lockstep only pays when the sweep is write-bound, i.e. when few slices hold obstacles; with obstacles in most slices the
+    // envelope work per step varies a lot between warps and the per-step barrier costs more than the locality gains.
     __shared__ int s_item;
+    const bool lockstep = ns * 4 <= Z;
     const int XG8 = (XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     for (;;) {
         __syncthreads();
@@ -378,7 +381,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             continue;
         }
         if (xg >= XG) {   // ragged last group of the row: keep the barrier count of the lockstep loop below
-            for (int u = Z - 1; u >= 0; u--) __syncthreads();
+            if (lockstep) for (int u = Z - 1; u >= 0; u--) __syncthreads();
             continue;
         }
         int q = -1;
@@ -421,7 +424,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
         unsigned long long *pp = m.pair + base + (size_t)(Z - 1) * slice;
         for (int u = Z - 1; u >= 0; u--) {
-            __syncthreads();
+            if (lockstep) __syncthreads();
             if (valid) {
                 const int d = u - top.s;
                 const int dist = d * d + top.h;

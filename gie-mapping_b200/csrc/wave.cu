@@ -16,7 +16,6 @@
 // identically by the CPU oracle.
 #include "engine.h"
 #include <cooperative_groups.h>
-#include <cuda/barrier>
 #include <algorithm>
 
 namespace {
@@ -198,44 +197,28 @@ __device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev
 
 // MarkLimitedObserve (unify_helper.cuh:201-273) for the known voxels: where the batch EDT found something farther than the
 // distance the global map remembers to an obstacle that has left the volume, keep the remembered one.
-// The block's remembered distances and closest obstacles (2 KB + 4 KB, contiguous in the field-major pools) are staged into
-// shared memory with two TMA bulk copies (cp.async.bulk, completion on an mbarrier) per CTA pass.
 __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ n_slices, const int *__restrict__ list,
                                                      const int *__restrict__ count)
 {
-    using barrier_t = cuda::barrier<cuda::thread_scope_block>;
-    __shared__ alignas(16) int32_t s_dist[512];
-    __shared__ alignas(16) unsigned long long s_coc[512];
-#pragma nv_diag_suppress static_var_with_dynamic_init
-    __shared__ barrier_t bar;
-    if (threadIdx.x == 0) { init(&bar, blockDim.x); cuda::device::experimental::fence_proxy_async_shared_cta(); }
-    __syncthreads();
     if (__ldcg(n_slices) == 0) return;   // k_mark handles the obstacle-free volume
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
         const int blk = __ldcg(&h.btab[ti]);
-        barrier_t::arrival_token tok;
-        if (threadIdx.x == 0) {
-            cuda::device::memcpy_async_tx(s_dist, h.dist_sq + (size_t)blk * 512, cuda::aligned_size_t<16>(sizeof(s_dist)), bar);
-            cuda::device::memcpy_async_tx(s_coc, h.coc_glb + (size_t)blk * 512, cuda::aligned_size_t<16>(sizeof(s_coc)), bar);
-            tok = cuda::device::barrier_arrive_tx(bar, 1, sizeof(s_dist) + sizeof(s_coc));
-        } else tok = bar.arrive();
-        bar.wait(std::move(tok));
         for (int v = threadIdx.x; v < 512; v += blockDim.x) {
             int3 c;
             if (!block_voxel_local(m, h, ti, v, c)) continue;
             const int id = gie_lidx(m, c);
             if (m.glb_type[id] == GIE_VOX_UNKNOWN) continue;
-            const int dist_new = m.aux[id], dist_old = s_dist[v];
+            const size_t vi = (size_t)blk * 512 + v;
+            const int dist_new = m.aux[id], dist_old = h.dist_sq[vi];
             if (!(dist_new > dist_old)) continue;
-            const int3 coc_buf_old = gie_unpack_coc(s_coc[v]) - m.pvt;
+            const int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
             if (gie_inside_loc(m, coc_buf_old)) continue;
             const int3 wr = coc_buf_old + m.pvt - m.upvt;
             if (!gie_inside_wr(wr)) { m.pair[id] = gie_mk_pair(GIE_EMPTY_VALUE, GIE_INVALID_ID_STALE); m.aux[id] = GIE_EMPTY_VALUE; }
             else { m.pair[id] = gie_mk_pair(dist_old, gie_wr2id(wr)); m.aux[id] = dist_old; }
         }
-        __syncthreads();   // the staging buffers are free for the next block
     }
 }
 
