@@ -3,7 +3,11 @@
 // own operator surface (LocMap, GlbHashMap, EDT_OCC::batchEDTUpdate, *::localOGMKernels, Ext_Obs_Wrapper, warmupCuda,
 // cuttPlan) as provided by include/gie_compat/ over the C ABI of libgie_b200.so.  Plain C++17, built with g++.
 //
-//   gie_replay <frames.bin> <out.bin|-> [--time] [--stream] [--costmap]
+//   gie_replay <frames.bin> <out.bin|-> [--time] [--stream] [--costmap] [--mapmakers]
+//
+// --mapmakers routes the sensor data through the node-level front ends (PntcldMapMaker / HokuyoMapMaker / RealsenseMapMaker
+// ::updateLocalOGM on HOST payloads, as VOLMAPNODE does at volumetric_mapper.cpp:158-176) instead of calling
+// XXX::localOGMKernels on a device buffer.
 //
 // frames.bin (little endian; writer: gie-mapping_b200/replay_io.py):
 //   header  int32[18] {magic 'GIE1', sensor, X, Y, Z, occupancy_threshold, cutoff_grids_sq, fast_mode, bucket_max,
@@ -28,6 +32,10 @@
 #include "kernel/hokuyo/hokuyo_interfaces.h"
 #include "kernel/vlp16/vlp16_interface.h"
 #include "kernel/realsense/realsense_interfaces.h"
+#include "cuda_toolkit/occupancy/point_cloud/pntcld_map_maker.h"
+#include "cuda_toolkit/occupancy/hokuyo/hokuyo_map_maker.h"
+#include "cuda_toolkit/occupancy/realsense/realsense_map_maker.h"
+#include "cuda_toolkit/occupancy/vlp16/vlp16_map_maker.h"
 
 namespace {
 struct Header {
@@ -56,11 +64,12 @@ void dump(FILE *fo, LocMap &m, int which, std::vector<T> &buf)
 int main(int argc, char **argv)
 {
     if (argc < 3) { fprintf(stderr, "usage: %s frames.bin out.bin|- [--time] [--stream] [--costmap]\n", argv[0]); return 2; }
-    bool timing = false, stream = false, costmap = false;
+    bool timing = false, stream = false, costmap = false, mapmakers = false;
     for (int i = 3; i < argc; i++) {
         if (!strcmp(argv[i], "--time")) timing = true;
         else if (!strcmp(argv[i], "--stream")) stream = true;
         else if (!strcmp(argv[i], "--costmap")) costmap = true;
+        else if (!strcmp(argv[i], "--mapmakers")) mapmakers = true;
     }
     FILE *fi = fopen(argv[1], "rb");
     Header h;
@@ -86,6 +95,13 @@ int main(int argc, char **argv)
         GlbHashMap *hash_map = new GlbHashMap(loc_map->_bdr_num, loc_map->_local_size, h.bucket_max, h.block_max);
         hash_map->setLocMap(loc_map);
         Ext_Obs_Wrapper *ext_obs = new Ext_Obs_Wrapper(1);
+        PntcldMapMaker pnt_map_maker;
+        HokuyoMapMaker hok_map_maker;
+        RealsenseMapMaker rea_map_maker;
+        pnt_map_maker.setLocMap(loc_map); hok_map_maker.setLocMap(loc_map); rea_map_maker.setLocMap(loc_map);
+        pnt_map_maker.initialize(PntcldParam((int)(max_payload / 3)));
+        hok_map_maker.initialize(ScanParam(h.scan_num, 30.f, h.theta_inc, h.theta_min));
+        rea_map_maker.initialize(CamParam(h.rows, h.cols, h.cx, h.cy, h.fx, h.fy, h.valid_nan != 0));
         warmupCuda();
 
         float *sensor_dev = nullptr;   // the MapMakers' device buffer (e.g. PntcldMapMaker::_gpu_cld)
@@ -105,8 +121,15 @@ int main(int argc, char **argv)
             loc_map->calculate_update_pivot(proj.origin);
             int3 *keys = hash_map->VB_keys_loc_D.data();
             const int n = (int)f.payload.size();
-            if (n) cudaMemcpy(sensor_dev, f.payload.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
-            if (h.sensor == 0) {
+            const bool via_maker = mapmakers && h.sensor != 2;   // the VLP-16 maker wants the raw cloud, the frame file holds range images
+            if (n && !via_maker) cudaMemcpy(sensor_dev, f.payload.data(), (size_t)n * sizeof(float), cudaMemcpyHostToDevice);
+            if (via_maker && h.sensor == 0) {
+                pnt_map_maker.updateLocalOGM(proj, (const uint8_t *)f.payload.data(), n / 3, 12, 0, keys, time, h.fmp != 0, h.r2);
+            } else if (via_maker && h.sensor == 1) {
+                hok_map_maker.updateLocalOGM(proj, f.payload.data(), keys, time, h.fmp != 0, h.r2);
+            } else if (via_maker && h.sensor == 3) {
+                rea_map_maker.updateLocalOGM(proj, f.payload.data(), keys, time, h.fmp != 0, h.r2);
+            } else if (h.sensor == 0) {
                 PntcldParam pp(n / 3);
                 pp.valid_pnt_count = n / 3;
                 PNTCLD_RAYCAST::localOGMKernels(loc_map, (float3 *)sensor_dev, proj, pp, keys, time, h.fmp != 0, h.r2);

@@ -60,7 +60,7 @@ def read_output(path, cfg, nframes, stream=False, costmap=False):
     return out, mirror
 
 
-def run_replay(cfg, frames, workdir, stream=False, costmap=False, timing=False):
+def run_replay(cfg, frames, workdir, stream=False, costmap=False, timing=False, mapmakers=False):
     """Runs the C++ host driver on the frames; returns (per-frame arrays, streamed host mirror or None, stdout)."""
     exe = replay_binary()
     if not os.path.exists(exe):
@@ -68,7 +68,8 @@ def run_replay(cfg, frames, workdir, stream=False, costmap=False, timing=False):
     inp, outp = os.path.join(workdir, "frames.bin"), os.path.join(workdir, "out.bin")
     write_frames(inp, cfg, frames)
     # timing runs dump nothing (the per-frame arrays of a 512^3 volume are 2.8 GB)
-    cmd = [exe, inp, "-" if timing else outp] + (["--stream"] if stream else []) + (["--costmap"] if costmap else []) + (["--time"] if timing else [])
+    cmd = [exe, inp, "-" if timing else outp] + (["--stream"] if stream else []) + (["--costmap"] if costmap else []) + (["--time"] if timing else []) + \
+          (["--mapmakers"] if mapmakers else [])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"gie_replay failed ({res.returncode}): {res.stdout[-1000:]} {res.stderr[-2000:]}")

@@ -180,14 +180,17 @@ def test_stream_pipeline_matches_oracle(gie, oracle):
             om.close()
 
 
+@pytest.mark.parametrize("mapmakers", [False, True], ids=["kernels", "mapmakers"])
 @pytest.mark.parametrize("name,size,cutoff", [("cfg4", (48, 48, 24), 64), ("cfg1", (64, 64, 16), 100), ("cfg2", (64, 64, 32), 49),
                                               ("cfg3", (64, 64, 32), 100)])
-def test_cpp_host_replay_parity(gie, oracle, tmp_path, name, size, cutoff):
+def test_cpp_host_replay_parity(gie, oracle, tmp_path, name, size, cutoff, mapmakers):
     """The C++ host driver (reference operator surface from include/gie_compat over the C ABI) against the oracle, frame by
     frame, plus the host mirror of the global map that streamPipeline maintains and the CostMap payload."""
     cfg = gie.scenes.small_config(name, size, cutoff_grids_sq=cutoff)
     frames = gie.scenes.make_frames(cfg, 5, dynamic=True)
-    out, mirror, _ = gie.replay_io.run_replay(cfg, frames, str(tmp_path), stream=True, costmap=True)
+    if mapmakers and name == "cfg2":
+        pytest.skip("the VLP-16 MapMaker takes the raw cloud (test_pointcloud2_front_ends); the frame file holds range images")
+    out, mirror, _ = gie.replay_io.run_replay(cfg, frames, str(tmp_path), stream=True, costmap=True, mapmakers=mapmakers)
     cfg_o = dict(cfg); cfg_o["display_glb_edt"] = True
     om = oracle.OracleMapper(cfg_o)
     omirror = {}
