@@ -170,3 +170,12 @@ def test_compat_host_logic_cpp(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "compat host checks OK" in res.stdout
+
+
+def test_compat_ros_typed_overloads_compile(tmp_path):
+    """The ROS-typed overloads (GIE_COMPAT_WITH_ROS / GIE_COMPAT_WITH_TF) compile against minimal message stand-ins: ROS is not
+    installed in this image, so this is the closest check that a maintainer's node would build against include/gie_compat."""
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-DGIE_COMPAT_WITH_ROS", "-DGIE_COMPAT_WITH_TF",
+                           f"-I{inc}/gie_compat", f"-I{inc}", "-I/usr/local/cuda/include", f"-I{ROOT}/tests/cpp/ros_stubs",
+                           f"-I{ROOT}/oracle/ref_harness/stubs", os.path.join(ROOT, "tests", "cpp", "test_compat_ros_overloads.cpp")])
