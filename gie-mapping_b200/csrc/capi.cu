@@ -54,6 +54,17 @@ int check_frame_args(gie_locmap *lm, gie_hashmap *hm)
     return GIE_OK;
 }
 
+// The device status word is sticky and is mirrored into pinned host memory at the end of every merge (k_wave_stats), so the
+// per-frame entry points can refuse to go on after the block pool ran out WITHOUT a device synchronisation.  The reference
+// throws "out of block memory" from its host-side allocator at once (blockalloc.h:56-58); here the failure surfaces on the
+// next call after the frame that hit it, and gie_sync() reports it immediately.
+int check_sticky_status(gie_hashmap *hm)
+{
+    const long long st = *(volatile long long *)&hm->stats_host[8];
+    if (st & (GIE_DEV_ERR_OUT_OF_BLOCKS | GIE_DEV_ERR_HASH_FULL)) { gie_set_error("out of block memory (raise block_max)"); return GIE_ERR_OUT_OF_BLOCKS; }
+    return GIE_OK;
+}
+
 struct ArrInfo { void *p; size_t bytes; };
 ArrInfo arr_info(gie_locmap *lm, int which)
 {
@@ -313,9 +324,9 @@ int gie_hashmap_create(gie_hashmap **out, gie_locmap *lm, int bucket_max, int bl
     GIE_CUDA_CHECK(cudaMalloc(&hm->changed_list, (size_t)block_max * sizeof(int)));
     GIE_CUDA_CHECK(cudaMalloc(&hm->changed_count, sizeof(int)));
     GIE_CUDA_CHECK(cudaMallocHost(&hm->status_host, sizeof(int)));
-    GIE_CUDA_CHECK(cudaMallocHost(&hm->stats_host, 8 * sizeof(long long)));
+    GIE_CUDA_CHECK(cudaMallocHost(&hm->stats_host, 16 * sizeof(long long)));
     *hm->status_host = 0;
-    memset(hm->stats_host, 0, 8 * sizeof(long long));
+    memset(hm->stats_host, 0, 16 * sizeof(long long));
     if ((rc = gie_wave_prepare(hm)) != GIE_OK) return rc;
     lm->hm = hm;
     if ((rc = gie_hash_begin_frame(hm)) != GIE_OK) return rc;
@@ -471,6 +482,7 @@ int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int st
                            const float *obs_ur, const unsigned char *obs_activated)
 {
     if (!hm || n_obs < 0 || (n_obs > 0 && (!obs_ll || !obs_ur || !obs_activated))) return GIE_ERR_INVALID_ARG;
+    { int rc = check_sticky_status(hm); if (rc != GIE_OK) return rc; }
     // only activated boxes travel (Ext_Obs_Wrapper::bbx_H2D uploads all of them every frame, pre_map.cu:50-60);
     // slot 0 keeps its meaning as the fence even when it is off
     int n_dev = 0;
@@ -514,6 +526,7 @@ int gie_edt_z_sweep(gie_locmap *lm, int max_width_override)
 int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt)
 {
     if (!hm) return GIE_ERR_INVALID_ARG;
+    { int rc = check_sticky_status(hm); if (rc != GIE_OK) return rc; }
     return gie_launch_merge(hm, map_ct, display_glb_edt);
 }
 

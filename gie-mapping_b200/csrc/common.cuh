@@ -26,6 +26,7 @@
 #define GIE_DEV_ERR_OUT_OF_BLOCKS 1
 #define GIE_DEV_ERR_QUEUE_OVERFLOW 2
 #define GIE_DEV_ERR_HASH_FULL 4
+#define GIE_HASH_POISON 0x7fffffff   // value of a key slot whose insert found the block pool exhausted
 
 struct LocDev {
     int X, Y, Z, N;
@@ -144,17 +145,18 @@ __device__ __forceinline__ int gie_hash_find(const HashDev &h, int3 key)
 {
     unsigned long long k = gie_pack_key(key);
     uint32_t s = (uint32_t)gie_mix64(k) & h.cap_mask;
-    for (;;) {
+    for (uint32_t probes = 0; probes <= h.cap_mask; probes++) {   // bounded: a full table ends the walk
         unsigned long long cur = __ldcg(&h.keys[s]);
         if (cur == k) {
             int v;
             // the value is published after the key; spin until visible (insert is two stores)
             while ((v = *(volatile int32_t *)&h.vals[s]) < 0) { }
-            return v;
+            return v == GIE_HASH_POISON ? -1 : v;   // key claimed while the block pool was exhausted: no block behind it
         }
         if (cur == ~0ULL) return -1;
         s = (s + 1) & h.cap_mask;
     }
+    return -1;
 }
 // block index for a global voxel coordinate: dense table first, hash probe outside it
 __device__ __forceinline__ int gie_block_of(const HashDev &h, int3 glb)

@@ -353,7 +353,6 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     const int X = m.X, Z = m.Z, S = m.max_width;
     const size_t slice = (size_t)X * m.Y;
     const int ns = __ldg(n_slices);
-    const int3 wr0 = m.pvt - m.upvt;   // local coords -> wave-range coords
     // A CTA takes WARPS_PER_CTA adjacent 32-wide x groups of one row y at a time and its warps walk z in lockstep (one
     // __syncthreads per z step), so that every step the CTA writes ONE contiguous run per output array (1 KB / 1 KB / 2 KB at
     // 8 warps) instead of eight unrelated 128-byte lines at eight different depths: the sweep is bound by its 16 B/voxel of
@@ -404,38 +403,29 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             int k = __ldg(&slice_list[j]);
             envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
         }
-        // backward (local_edt_core.h:169-192).  Besides _aux / _coc_idx_aux the sweep also writes the (dist, wave-range coc
-        // id) pair every voxel starts the merge with (the UNKNOWN-voxel half of MarkLimitedObserve, unify_helper.cuh:201-273),
-        // which saves a 17 B/voxel pass over the volume; k_mark then only patches known voxels.
-        // Everything except the distance is constant along one envelope segment (one owner slice), so it is recomputed only when
-        // the owner changes; a z step is then d*d + h, three streaming stores and pointer bumps.
+        // backward (local_edt_core.h:169-192).  The coc word is constant along one envelope segment (one owner slice), so it
+        // is recomputed only when the owner changes; a z step is then d*d + h, two streaming stores and pointer bumps.
+        // (_dist_id_pair is NOT written here: the reference leaves the pair of UNKNOWN voxels stale and the wavefronts relax
+        // against those stale words, so only k_mark_blocks writes it, for known voxels — unify_helper.cuh:217-218.)
         int c = __ldg(&cxy[base + (size_t)top.s * slice]);
-        int coc_word = 0;
-        uint32_t pid = 0;
-        bool wr_ok = false;
-        auto owner_changed = [&]() {
-            coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
-            int3 wr = make_int3((c & 0xffff) + wr0.x, (c >> 16) + wr0.y, top.s + wr0.z);
-            wr_ok = gie_inside_wr(wr);
-            pid = wr_ok ? gie_wr2id(wr) : GIE_INVALID_ID_STALE;
-        };
-        owner_changed();
+        int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
         int32_t *pa = m.aux + base + (size_t)(Z - 1) * slice;
         int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
-        unsigned long long *pp = m.pair + base + (size_t)(Z - 1) * slice;
         for (int u = Z - 1; u >= 0; u--) {
             if (lockstep) __syncthreads();
             if (valid) {
                 const int d = u - top.s;
-                const int dist = d * d + top.h;
-                __stcs(pa, dist);
+                __stcs(pa, d * d + top.h);
                 __stcs(pc, coc_word);
-                __stcs(pp, gie_mk_pair(wr_ok ? dist : GIE_EMPTY_VALUE, pid));
             }
-            pa -= slice; pc -= slice; pp -= slice;
+            pa -= slice; pc -= slice;
             if (u == top.t) {
                 q--;
-                if (q >= 0) { top = st.get(q); c = __ldg(&cxy[base + (size_t)top.s * slice]); owner_changed(); }
+                if (q >= 0) {
+                    top = st.get(q);
+                    c = __ldg(&cxy[base + (size_t)top.s * slice]);
+                    coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+                }
             }
         }
     }

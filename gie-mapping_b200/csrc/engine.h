@@ -46,6 +46,7 @@ struct gie_hashmap {
     int queue_cap = 0;
     int *counters = nullptr;      // device ints, see wave.cu
     unsigned int *barrier = nullptr;
+    size_t barrier_words = 0;
     // decision scratch for wave A (parallel to the current queue)
     int32_t *decA_dist = nullptr;
     unsigned long long *decA_coc = nullptr;
@@ -67,7 +68,7 @@ struct gie_hashmap {
     int *changed_list = nullptr;
     int *changed_count = nullptr;
     int *status_host = nullptr;   // pinned
-    long long *stats_host = nullptr;  // pinned [8]
+    long long *stats_host = nullptr;  // pinned [16]: wave statistics [0..7], sticky device status [8]
 };
 
 void gie_set_error(const std::string &msg);

@@ -32,12 +32,14 @@ __device__ int hash_insert(const HashDev &h, int3 key)
     for (uint32_t probes = 0; probes <= h.cap_mask; probes++) {
         unsigned long long cur = __ldcg(&h.keys[s]);
         if (cur == ~0ULL) {
+            // pool already exhausted: do not burn a key slot for an insert that cannot succeed
+            if (*(volatile int *)h.block_count >= h.block_max) { atomicOr(h.status, GIE_DEV_ERR_OUT_OF_BLOCKS); return -1; }
             unsigned long long prev = atomicCAS(&h.keys[s], ~0ULL, k);
             if (prev == ~0ULL) {
                 int b = atomicAdd(h.block_count, 1);
                 if (b >= h.block_max) {
                     atomicOr(h.status, GIE_DEV_ERR_OUT_OF_BLOCKS);
-                    atomicExch(&h.vals[s], 0x7fffffff);   // poison: readers stop spinning
+                    atomicExch(&h.vals[s], GIE_HASH_POISON);   // poison: readers stop spinning and see "no block"
                     return -1;
                 }
                 h.block_keys[b] = key;
@@ -50,7 +52,7 @@ __device__ int hash_insert(const HashDev &h, int3 key)
         if (cur == k) {
             int v;
             while ((v = *(volatile int32_t *)&h.vals[s]) < 0) { }   // volatile: the publish comes from another thread
-            return v == 0x7fffffff ? -1 : v;
+            return v == GIE_HASH_POISON ? -1 : v;
         }
         s = (s + 1) & h.cap_mask;
     }

@@ -12,7 +12,7 @@
 // Mechanism: ONE persistent cooperative kernel runs wave A, B and C back to back with a device-side grid barrier
 // between BFS levels and global ring queues; there is no host round trip inside a frame.  The relaxation is a 64-bit
 // atomicMin on (dist_sq << 32 | coc id), which also makes the result independent of thread scheduling — the reference
-// is schedule dependent here; the deterministic rules D1-D4 are listed in DESIGN.md §5 and are restated
+// is schedule dependent here; the deterministic rules D1-D3, D5 are listed in DESIGN.md §3.2 and are restated
 // identically by the CPU oracle.
 #include "engine.h"
 #include <cooperative_groups.h>
@@ -34,6 +34,7 @@ struct LocalQ {
     int n[2];
     int total, nmax;
     int spill_base;
+    int n0, gather;   // hand-off to the solo mode: CTA 0's own count as every CTA read it / entries gathered from the peers
     int solo_level, solo_cb;
 };
 constexpr int SOLO_ENTER = 256;   // frontier size at or below which ONE CTA runs the levels alone (6 * 256 pushes fit LQ_CAP)
@@ -107,64 +108,6 @@ __device__ __forceinline__ bool q_push(T *q, int *cnt, int cap, T v, int *status
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// MarkLimitedObserve (unify_helper.cuh:201-273).  Each thread owns VEC consecutive voxels along x (vector loads/stores),
-// grid-stride over a grid sized to the SM count.  D4: UNKNOWN voxels get their batch values instead of stale memory.
-template <int VEC>
-__global__ void __launch_bounds__(256) k_mark(LocDev m, HashDev h, const int *__restrict__ n_slices)
-{
-    // Full-volume form, only needed while the volume holds no obstacle at all ("sees nothing" sentinels everywhere);
-    // otherwise the z sweep has written every voxel's starting pair and k_mark_blocks patches the known voxels.
-    if (__ldcg(n_slices) > 0) return;
-    const int nq = m.N / VEC;
-    const int mw = m.max_width;
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
-        const int id0 = q * VEC;
-        const int x0 = id0 % m.X, yz = id0 / m.X;
-        const int y = yz % m.Y, z = yz / m.Y;
-        int8_t type[VEC]; int dist[VEC], cocv[VEC];
-        unsigned long long pr[VEC];
-        if (VEC == 4) {
-            char4 t4 = *reinterpret_cast<const char4 *>(m.glb_type + id0);
-            int4 a4 = *reinterpret_cast<const int4 *>(m.aux + id0);
-            int4 c4 = *reinterpret_cast<const int4 *>(m.coc_aux + id0);
-            type[0] = t4.x; type[1] = t4.y; type[2] = t4.z; type[3] = t4.w;
-            dist[0] = a4.x; dist[1] = a4.y; dist[2] = a4.z; dist[3] = a4.w;
-            cocv[0] = c4.x; cocv[1] = c4.y; cocv[2] = c4.z; cocv[3] = c4.w;
-        } else { type[0] = m.glb_type[id0]; dist[0] = m.aux[id0]; cocv[0] = m.coc_aux[id0]; }
-#pragma unroll
-        for (int k = 0; k < VEC; k++) {
-            const int3 c = make_int3(x0 + k, y, z);
-            int3 coc_new = gie_id2wr((uint32_t)cocv[k]);   // same 11/11/10 packing, local coords
-            const int dist_new = dist[k];
-            int aux = dist_new;
-            uint32_t pid = 0;
-            int pdist = 0;
-            const bool see_nothing = coc_new.x > mw || coc_new.y > mw || coc_new.z > mw;   // invalid_coc_buf, voxmap_utils.cuh:174-179
-            if (see_nothing) { pdist = GIE_EMPTY_VALUE; pid = 0xffffffffu; aux = GIE_EMPTY_VALUE; }
-            if (type[k] != GIE_VOX_UNKNOWN) {
-                int3 glb = c + m.pvt;
-                int blk = gie_block_of(h, glb);
-                if (blk >= 0) {   // a known voxel always has a block
-                    size_t vi = (size_t)blk * 512 + gie_vox_in_block(glb);
-                    int dist_old = h.dist_sq[vi];
-                    int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
-                    if (dist_new > dist_old && !gie_inside_loc(m, coc_buf_old)) { coc_new = coc_buf_old; aux = dist_old; }
-                }
-            }
-            int3 wr = coc_new + m.pvt - m.upvt;
-            if (!gie_inside_wr(wr)) { pdist = GIE_EMPTY_VALUE; aux = GIE_EMPTY_VALUE; if (!see_nothing) pid = GIE_INVALID_ID_STALE; }
-            else { pdist = aux; pid = gie_wr2id(wr); }
-            pr[k] = gie_mk_pair(pdist, pid);
-            if (aux != dist_new) m.aux[id0 + k] = aux;
-        }
-        if (VEC == 4) {
-            ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(m.pair + id0);
-            dst[0] = make_ulonglong2(pr[0], pr[1]);
-            dst[1] = make_ulonglong2(pr[2], pr[3]);
-        } else m.pair[id0] = pr[0];
-    }
-}
-
 // The per-voxel kernels of the merge (frontiers, commit) walk the ALLOCATED blocks that intersect the local volume instead
 // of the whole volume: a known voxel always has a block, and in the headline scene the allocated blocks cover ~5 % of the
 // 512^3 volume.  k_list_blocks compacts the dense block table into that list once per merge; the kernels then take one
@@ -195,13 +138,18 @@ __device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev
     return gie_inside_loc(m, c);
 }
 
-// MarkLimitedObserve (unify_helper.cuh:201-273) for the known voxels: where the batch EDT found something farther than the
-// distance the global map remembers to an obstacle that has left the volume, keep the remembered one.
-__global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ n_slices, const int *__restrict__ list,
-                                                     const int *__restrict__ count)
+// MarkLimitedObserve (unify_helper.cuh:201-273).  The reference skips UNKNOWN voxels altogether (:217-218): their
+// _dist_id_pair keeps whatever an earlier frame left at that local index, and the wavefronts later relax against those
+// stale words.  That is deterministic and is reproduced here: the pair array is written for KNOWN voxels only (and by the
+// waves), never cleared.  A known voxel always has a block, so the kernel walks the allocated blocks that intersect the
+// volume.  Per known voxel: start from the batch result; "sees nothing" (no obstacle in the volume) -> (EMPTY, 0xffffffff);
+// where the batch EDT found something farther than the distance the global map remembers to an obstacle that has left the
+// volume, keep the remembered one; a coc outside the wave range invalidates the distance word only (the id word stays
+// stale, :258-261).
+__global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ list, const int *__restrict__ count)
 {
-    if (__ldcg(n_slices) == 0) return;   // k_mark handles the obstacle-free volume
     const int n = __ldcg(count);
+    const int mw = m.max_width;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
         const int blk = __ldcg(&h.btab[ti]);
@@ -212,12 +160,22 @@ __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const 
             if (m.glb_type[id] == GIE_VOX_UNKNOWN) continue;
             const size_t vi = (size_t)blk * 512 + v;
             const int dist_new = m.aux[id], dist_old = h.dist_sq[vi];
-            if (!(dist_new > dist_old)) continue;
-            const int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
-            if (gie_inside_loc(m, coc_buf_old)) continue;
-            const int3 wr = coc_buf_old + m.pvt - m.upvt;
-            if (!gie_inside_wr(wr)) { m.pair[id] = gie_mk_pair(GIE_EMPTY_VALUE, GIE_INVALID_ID_STALE); m.aux[id] = GIE_EMPTY_VALUE; }
-            else { m.pair[id] = gie_mk_pair(dist_old, gie_wr2id(wr)); m.aux[id] = dist_old; }
+            int3 coc_new = gie_id2wr((uint32_t)m.coc_aux[id]);   // same 11/11/10 packing, local coords
+            int aux = dist_new, pdist;
+            uint32_t pid;
+            bool have_id = false;
+            if (coc_new.x > mw || coc_new.y > mw || coc_new.z > mw) { pid = 0xffffffffu; have_id = true; aux = GIE_EMPTY_VALUE; }   // invalid_coc_buf
+            if (dist_new > dist_old) {
+                const int3 coc_buf_old = gie_unpack_coc(h.coc_glb[vi]) - m.pvt;
+                if (!gie_inside_loc(m, coc_buf_old)) { coc_new = coc_buf_old; aux = dist_old; }
+            }
+            const int3 wr = coc_new + m.pvt - m.upvt;
+            if (!gie_inside_wr(wr)) {
+                pdist = GIE_EMPTY_VALUE; aux = GIE_EMPTY_VALUE;
+                if (!have_id) pid = gie_pair_id(m.pair[id]);     // stale id word
+            } else { pdist = aux; pid = gie_wr2id(wr); }
+            m.pair[id] = gie_mk_pair(pdist, pid);
+            if (aux != dist_new) m.aux[id] = aux;
         }
     }
 }
@@ -653,7 +611,7 @@ __device__ int wave_c_local(const LocDev &m, const HashDev &h, const WaveDev &w,
             uint32_t sid = gie_pair_id(__ldcg(&m.pair[gie_lidx(m, c_entry_coord(e))]));
             lq.snap[k] = (want == C_ALWAYS || want == sid) ? sid : 0xffffffffu;
         }
-        if (t == 0) lq.n[cb ^ 1] = 0;
+        if (t == 0) { lq.n[cb ^ 1] = 0; lq.gather = 0; }
         if (tr) w.trace[level * 6 + 2] = gtimer();
         cl.sync();   // all snapshots taken, all next-queue counters zero
         if (tr) w.trace[level * 6 + 3] = gtimer();
@@ -714,23 +672,27 @@ __device__ int wave_c_local(const LocDev &m, const HashDev &h, const WaveDev &w,
             int sum = c, mx = c;
 #pragma unroll
             for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
-            if (t == 0) { lq.total = sum; lq.nmax = mx; }
+            const int c0 = __shfl_sync(0xffffffffu, c, 0);
+            if (t == 0) { lq.total = sum; lq.nmax = mx; lq.n0 = c0; }
         }
         __syncthreads();
         if (tr) w.trace[(level - 1) * 6 + 5] = gtimer();
         int total = lq.total, nmax = lq.nmax;
         if (total > 0 && total <= SOLO_ENTER && nmax <= LQ_CAP && !w.no_solo) {
             // hand the whole frontier to CTA 0 and let it run alone (wave_c_solo); the other CTAs park at the cluster barrier
+            // Nothing below may touch a queue counter of this level (lq.n[cb]) before the next cluster barrier: a slower
+            // CTA can still be reading all of them (above) and must reach the same decision.  The hand-off therefore counts
+            // in a separate word of CTA 0 (lq.gather, zeroed by CTA 0 in phase 1) on top of CTA 0's own count n0.
             if (r != 0) {
                 const int mine = lq.n[cb];
-                if (t == 0) lq.spill_base = mine ? atomicAdd(cl.map_shared_rank(&lq.n[cb], 0), mine) : 0;
+                if (t == 0) lq.spill_base = lq.n0 + (mine ? atomicAdd(cl.map_shared_rank(&lq.gather, 0), mine) : 0);
                 __syncthreads();
                 unsigned long long *q0 = cl.map_shared_rank(&lq.q[cb][0], 0);
                 for (int k = t; k < mine; k += T) q0[lq.spill_base + k] = lq.q[cb][k];
-                __syncthreads();
-                if (t == 0) { lq.n[0] = 0; lq.n[1] = 0; }
             }
-            cl.sync();
+            cl.sync();   // every CTA has decided, all copies have landed
+            if (r != 0) { if (t == 0) { lq.n[0] = 0; lq.n[1] = 0; } }
+            else { if (t == 0) lq.n[cb] += lq.gather; __syncthreads(); }
             if (r == 0) {
                 level = wave_c_solo(m, h, w, lq, level, cb);
                 if (t == 0) { lq.solo_level = level; lq.solo_cb = cb; }
@@ -861,8 +823,9 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display
     }
 }
 
-__global__ void k_wave_stats(WaveDev w, long long *out)
+__global__ void k_wave_stats(WaveDev w, const int *status, long long *out)
 {
+    out[8] = *status;   // sticky device status, read by the next frame's entry points without a synchronisation
     out[0] = w.cnt[C_FA]; out[1] = w.cnt[C_FB]; out[2] = w.cnt[C_FC]; out[3] = w.cnt[C_LEVA]; out[4] = w.cnt[C_LEVB];
     out[5] = w.cnt[C_LEVC]; out[6] = w.cnt[C_FB_AFTER_A]; out[7] = w.cnt[C_FC_AFTER_B];
 }
@@ -929,7 +892,9 @@ int gie_wave_prepare(gie_hashmap *hm)
             cudaGetLastError();
         }
     }
-    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, (size_t)(hm->wave_ctas + 1) * 32 * sizeof(unsigned int)));
+    // sized for the larger of the cluster grid and the plain one-CTA-per-SM grid the launch falls back to (gie_launch_merge)
+    hm->barrier_words = (size_t)(std::max(hm->wave_ctas, lm->num_sms) + 1) * 32;
+    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, hm->barrier_words * sizeof(unsigned int)));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_dist, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_coc, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_pair, cap * 8));
@@ -944,6 +909,18 @@ int gie_wave_prepare(gie_hashmap *hm)
     return GIE_OK;
 }
 
+// refreshes blk_list / blk_count for callers outside the merge (check.cu)
+int gie_wave_list_blocks(gie_hashmap *hm)
+{
+    gie_locmap *lm = hm->lm;
+    const int entries = (int)hm->tab_entries;
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
+    k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, hm->blk_list, hm->blk_count);
+    lm->launches++;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
 int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
 {
     gie_locmap *lm = hm->lm;
@@ -951,23 +928,14 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     hm->merge_epoch++;
     WaveDev w = make_wave_dev(hm);
     w.display = display;
-    const int vec = (m.X % 4 == 0) ? 4 : 1;
-    long long groups = (long long)m.N / vec;
-    long long want = (groups + 255) / 256, cap = (long long)lm->num_sms * 16;
-    const int grid = (int)(want < cap ? want : cap);
     {
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->counters, 0, C_COUNT * sizeof(int), lm->stream));
-        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, (size_t)(hm->wave_ctas + 1) * 32 * sizeof(unsigned int), lm->stream));
+        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, hm->barrier_words * sizeof(unsigned int), lm->stream));
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
         const int entries = (int)hm->tab_entries;
         k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(m, hm->d, entries, hm->blk_list, hm->blk_count);
-        const int *n_slices = lm->edt_meta + 2 * m.Z;
-        // (grid-stride kernel that returns at once unless the volume holds no obstacle: a small grid keeps the launch cheap)
-        const int grid_mark = std::min(grid, lm->num_sms * 4);
-        if (vec == 4) k_mark<4><<<grid_mark, 256, 0, lm->stream>>>(m, hm->d, n_slices);
-        else k_mark<1><<<grid_mark, 256, 0, lm->stream>>>(m, hm->d, n_slices);
-        k_mark_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, n_slices, hm->blk_list, hm->blk_count);
+        k_mark_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, hm->blk_list, hm->blk_count);
         k_frontiers<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
     }
     {
@@ -998,8 +966,8 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         StageTimer t(lm, GIE_ST_COMMIT);
         k_commit<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, display, hm->blk_list, hm->blk_count);
     }
-    k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->stats_host);
-    lm->launches += 7;
+    k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->d.status, hm->stats_host);
+    lm->launches += 6;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

@@ -35,6 +35,12 @@ class GieError(RuntimeError):
     pass
 
 
+class EdtCheck(C.Structure):
+    """gie_edt_check (include/gie_b200.h)."""
+    _fields_ = [("n", C.c_longlong), ("n_occupied", C.c_longlong), ("edt_less", C.c_longlong), ("edt_more", C.c_longlong),
+                ("sum_abs", C.c_double), ("sum_sq", C.c_double), ("max_abs", C.c_double), ("rms", C.c_double)]
+
+
 def library_path():
     return os.path.join(_HERE, "libgie_b200.so")
 
@@ -72,6 +78,7 @@ def load_library():
         "gie_sync": [p], "gie_hashmap_num_blocks": [p, C.POINTER(i)], "gie_hashmap_export_blocks": [p, p, p, i],
         "gie_hashmap_wave_stats": [p, p], "gie_profile_enable": [p, i], "gie_profile_last": [p, p],
         "gie_launch_count": [p, C.POINTER(C.c_longlong)], "gie_warmup": [],
+        "gie_hashmap_check_edt": [p, i, p, p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -313,6 +320,21 @@ class GlbHashMap:
         if n:
             _check(self.lib.gie_hashmap_export_blocks(self._h, _hostptr(keys), _hostptr(vox), n))
         return keys, vox
+
+    def check_edt(self, glb=False, want_truth=False):
+        """Gnd_truth_checker::cmp_dist (include/gt_checker.h:30-80) on the device.  Returns a dict of the error statistics
+        (metres) and, with want_truth (local mode only), the squared nearest-obstacle distance per local voxel (-1 = unchecked)."""
+        res = EdtCheck()
+        truth = None
+        if want_truth:
+            X, Y, Z = self._lMap._local_size
+            truth = np.empty(X * Y * Z, np.int32)
+        _check(self.lib.gie_hashmap_check_edt(self._h, int(glb), _hostptr(truth) if truth is not None else None, C.byref(res)))
+        out = {k: getattr(res, k) for k, _ in EdtCheck._fields_}
+        if truth is not None:
+            X, Y, Z = self._lMap._local_size
+            out["truth_sq"] = truth.reshape(Z, Y, X)
+        return out
 
     def wave_stats(self):
         out = np.zeros(8, np.int64)

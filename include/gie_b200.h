@@ -194,6 +194,25 @@ int gie_hashmap_export_blocks(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel 
 /* frontier sizes / BFS levels of the last merge: {fA, fB, fC, levelsA, levelsB, levelsC, fB_after_A, fC_after_B} */
 int gie_hashmap_wave_stats(gie_hashmap *hm, int64_t out8[8]);
 
+/* ---- self-validation ---------------------------------------------------------------------------- */
+/* Gnd_truth_checker::cmp_dist (include/gt_checker.h:30-80) evaluated on the device instead of through PCL clouds and a FLANN
+ * KD-tree on the host (include/volumetric_mapper.h:181-356).  For every voxel of the EDT cloud the exact distance to the
+ * nearest OCCUPIED voxel of the GLOBAL map is found (pruned brute force over voxel blocks) and compared with the distance
+ * the map holds: error = (nearest - edt) * voxel_width in metres.
+ *   mode 0 = profile_loc_rms: the known voxels of the local volume, edt = _edt_D
+ *   mode 1 = profile_glb_rms: every known hash voxel with a valid dist_sq, edt = sqrt(dist_sq)
+ *   truth_sq_host (mode 0 only, may be NULL): int32[X*Y*Z], squared nearest-obstacle distance in voxels per local voxel,
+ *                 -1 where the voxel is not part of the EDT cloud
+ * rms = sqrt(sum_sq / n) is cmp_dist's return value (-1 when either cloud is empty); edt_less / edt_more count the voxels
+ * whose EDT is more than 1 mm below / above the nearest-obstacle distance (l_cnt / m_cnt, gt_checker.h:55-58). */
+typedef struct gie_edt_check {
+    long long n;            /* voxels compared */
+    long long n_occupied;   /* OCCUPIED voxels in the global map */
+    long long edt_less, edt_more;
+    double sum_abs, sum_sq, max_abs, rms;
+} gie_edt_check;
+int gie_hashmap_check_edt(gie_hashmap *hm, int mode, int32_t *truth_sq_host, gie_edt_check *out);
+
 /* ---- measurement -------------------------------------------------------------------------------- */
 /* When enabled, CUDA events bracket each stage on the engine stream. */
 enum gie_stage { GIE_ST_OGM = 0, GIE_ST_HASH_MERGE = 1, GIE_ST_EDT_PACK = 2, GIE_ST_EDT_X = 3, GIE_ST_EDT_Z = 4,

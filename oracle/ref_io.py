@@ -41,22 +41,37 @@ def write_input(path, cfg, frames):
             f.write(p.tobytes())
 
 
-def read_output(path, cfg, nframes, halo):
+def iter_output(path, cfg, nframes, halo):
+    """Yields the per-frame outputs one at a time (a 512^3 frame is 2.8 GB)."""
     X, Y, Z = cfg["local_size"]
     n = X * Y * Z
     box = (Z + 2 * halo, Y + 2 * halo, X + 2 * halo)
-    out = []
     with open(path, "rb") as f:
         for _ in range(nframes):
             d = {}
-            d["glb_type"] = np.frombuffer(f.read(n), np.int8).reshape(Z, Y, X)
+            d["glb_type"] = np.fromfile(f, np.int8, n).reshape(Z, Y, X)
             for k in ["aux", "coc_aux", "pair_dist", "pair_id"]:
-                d[k] = np.frombuffer(f.read(4 * n), np.int32).reshape(Z, Y, X)
-            d["edt"] = np.frombuffer(f.read(4 * n), np.float32).reshape(Z, Y, X)
+                d[k] = np.fromfile(f, np.int32, n).reshape(Z, Y, X)
+            d["edt"] = np.fromfile(f, np.float32, n).reshape(Z, Y, X)
             nb = box[0] * box[1] * box[2]
-            d["box"] = np.frombuffer(f.read(nb * BOXVOX_DTYPE.itemsize), BOXVOX_DTYPE).reshape(box)
-            out.append(d)
-    return out
+            d["box"] = np.fromfile(f, BOXVOX_DTYPE, nb).reshape(box)
+            yield d
+
+
+def read_output(path, cfg, nframes, halo):
+    return list(iter_output(path, cfg, nframes, halo))
+
+
+def run_to_file(cfg, frames, flavour="parity", halo=4, workdir="/tmp"):
+    """Runs the reference driver and returns the path of its output file (read it with iter_output, then delete it)."""
+    inp = os.path.join(workdir, f"gie_ref_in_{os.getpid()}.bin")
+    outp = os.path.join(workdir, f"gie_ref_out_{os.getpid()}.bin")
+    write_input(inp, cfg, frames)
+    res = subprocess.run([driver_path(flavour), inp, outp, "--halo", str(halo)], capture_output=True, text=True)
+    os.remove(inp)
+    if res.returncode != 0:
+        raise RuntimeError(f"reference driver failed ({res.returncode}): {res.stdout[-2000:]} {res.stderr[-2000:]}")
+    return outp
 
 
 def run(cfg, frames, flavour="parity", halo=4, workdir="/tmp", timing=False):

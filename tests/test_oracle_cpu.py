@@ -64,9 +64,10 @@ def _cases():
 @pytest.mark.parametrize("path", _cases(), ids=lambda p: os.path.basename(p)[:-4])
 def test_oracle_vs_reference_golden(gie, oracle, path):
     """Frames before any wavefront activity must equal the reference bit-for-bit (occupancy, batch EDT after the
-    limited-observation pass, committed (dist, coc)).  Once the wavefronts run, the reference is schedule dependent and has
-    a missed-re-enqueue defect (wave_core.cuh:456-461), so we require >= 95 % identical voxels and that differing voxels
-    are in the majority CLOSER in the oracle (it converges further)."""
+    limited-observation pass, committed (dist, coc)).  Once the wavefronts run, equal-distance offers are resolved by
+    arrival order in the reference (id_atomicMin, wave_core.cuh:9-22) and by the smaller coc id here, which can move a
+    handful of distances by one step of the propagation: >= 99.9 % of the known voxels must carry the identical distance
+    (tests/test_wave_pinning_cpu.py holds the full accounting against ground truth)."""
     g = np.load(path)
     cfg = gie.scenes.small_config(str(g["cfg_name"]), tuple(int(v) for v in g["size"]), cutoff_grids_sq=int(g["cutoff"]))
     frames = gie.scenes.make_frames(cfg, int(g["nframes"]), dynamic=bool(g["dynamic"]))
@@ -94,11 +95,9 @@ def test_oracle_vs_reference_golden(gie, oracle, path):
             exact_frames += 1
         else:
             waves_seen = True
-            assert (om.glb_type != rt).sum() <= 8, f"frame {k}: glb_type differs in {(om.glb_type != rt).sum()} voxels"
+            assert (om.glb_type != rt).sum() <= 2, f"frame {k}: glb_type differs in {(om.glb_type != rt).sum()} voxels"
             same = (od[known] == rd[known]).mean()
-            assert same >= 0.95, f"frame {k}: only {same:.3f} of known voxels agree"
-            diff = (od - rd)[known & (od < 900000) & (rd < 900000)]
-            assert (diff < 0).sum() >= (diff > 0).sum(), f"frame {k}: oracle not closer: {(diff < 0).sum()} vs {(diff > 0).sum()}"
+            assert same >= 0.999, f"frame {k}: only {same:.5f} of known voxels agree"
     om.close()
     assert exact_frames >= 1
 
