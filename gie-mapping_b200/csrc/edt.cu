@@ -30,10 +30,6 @@ namespace {
 constexpr int WARPS_PER_CTA = 8;
 constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
 constexpr int RING = 16;      // stack entries per lane kept in shared memory
-constexpr int XB = 4;          // warps per x-sweep CTA = candidate bands = output x ranges of one (slice, 32 rows) item
-constexpr int XS_TILE_INTS = 2 * 32 * 17, XS_RING_INTS = 2 * RING * 32;
-constexpr int XS_SMEM_INTS_PER_WARP = XS_TILE_INTS + XS_RING_INTS + 64;   // tiles, stack ring, per-lane (q, base)
-constexpr int XS_SMEM_BYTES = XB * XS_SMEM_INTS_PER_WARP * 4;
 
 // y pass, step 1: OCCUPIED bits of 32 consecutive y per (z, wy, x) -> low word of ytab.  One thread per VEC adjacent words
 // (x fastest): 32 coalesced loads of VEC bytes in flight per thread, 128 bytes per warp instruction at VEC = 4.
@@ -192,149 +188,219 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
     }
 }
 
-// read-only view of the envelope stack another warp of the CTA has built (entries are private to a lane)
-struct StackView {
-    const int *sh, *sb;
-    const uint2 *g;
-    int base, q;
-    __device__ __forceinline__ Top read(int i) const
-    {
-        int hh, bb;
-        if (i >= base) { int sl = (i & (RING - 1)) * 32; hh = sh[sl]; bb = sb[sl]; }
-        else { uint2 v = g[i * 32]; hh = (int)v.x; bb = (int)v.y; }
-        Top e;
-        e.h = hh; e.s = bb & 0x3ff; e.t = (bb >> 10) & 0x3ff; e.cy = bb >> 20;
-        return e;
-    }
-};
-// push the entries of b (all to the right of everything on the stack) onto the stack: the same sequential algorithm, run on the
-// candidates that survived inside their own band
-__device__ __forceinline__ void merge_into(int &q, Top &top, LaneStack &st, const StackView &b, int L)
-{
-    const int qmax = __reduce_max_sync(0xffffffffu, b.q);
-    for (int i = 0; i <= qmax; i++)
-        if (i <= b.q) {
-            Top e = b.read(i);
-            envelope_push(e.s, e.h, e.cy, L, q, top, st);
-        }
-}
+// ---- x sweep (EDTphase2, local_edt_core.h:84-135) ---------------------------------------------------------------------
+// Work item = (obstacle-bearing slice z, RPI consecutive rows y); thread = (band b, row r).  The real columns of the slice
+// are cut into NB bands of at most CAP candidates.
+//   1. forward: every (band, row) thread builds the lower envelope of ITS band with the reference's sequential push
+//      (envelope_step), the whole stack in shared memory ([band][entry][row], conflict free).
+//   2. merge: parabolas of equal curvature cross exactly once, so the envelope of (left bands) U (right bands) is a prefix
+//      of the left envelope followed by a suffix of the right one.  Re-pushing the right envelope onto the left with the
+//      sequential algorithm would pop some top entries of the left, drop some first entries of the right, and then copy the
+//      rest unchanged — so only the cut is searched (a two-pointer loop of typically 1-3 steps) and recorded per band as
+//      (lo, hi, tfirst): the surviving entry range of the band's stack and the start of its first survivor.  Bands are merged
+//      pairwise in a tree (log2 NB rounds).  Same comparisons, same integer divisions, same tie behaviour as the push loop.
+//   3. backward (local_edt_core.h:116-134): x is cut into NB ranges; every (range, row) thread finds the entry that covers
+//      the end of its range in the composite envelope and walks down, emitting through a [RPI][TW] shared-memory tile so that
+//      global stores run along x.  This is the in-kernel transpose that replaces cuTT's {1,0,2} permutation and its inverse.
+// A serial scan of a 512-wide row is ~1000 dependent steps; here the dependent chain of an item is CAP + BW (+ merges)
+// ~ 70 steps, and a slice with few obstacle columns still keeps NB x 32 threads busy.
+struct XsCfg { int NB, CAP, BW, TW; };   // bands, stack capacity per band, x range per band (multiple of TW), tile width
 
-// x sweep (EDTphase2, local_edt_core.h:84-135).  One CTA of XB warps per (obstacle-bearing slice, 32 consecutive rows); lane =
-// row.  A slice holds few such items (36 slices x 16 row groups in the headline scene), so a single warp per item left the
-// GPU running one long dependent scan per scheduler.  Here the real columns of the slice are cut into XB bands; every warp
-// builds the lower envelope of its band, the band envelopes are merged pairwise with the same push step (a candidate that is
-// not on its band's envelope cannot be on the row's), and the backward pass is cut into XB ranges of x, each warp reading
-// the final stack of warp 0 and emitting through its own 32x16 tile.
-__global__ void __launch_bounds__(XB * 32)
+__device__ __forceinline__ int xs_meta_pack(int lo, int hi1, int tf) { return lo | (hi1 << 8) | (tf << 16); }
+#define XS_LO(mw) ((mw) & 0xff)
+#define XS_HI1(mw) (((mw) >> 8) & 0xff)      // hi + 1; the range [lo, hi] is empty when hi1 <= lo
+#define XS_TF(mw) ((mw) >> 16)
+
+template <int RPI>
+__global__ void __launch_bounds__(512)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
-             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, uint2 *__restrict__ scratch, int L,
-             int *__restrict__ work_counter)
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, XsCfg cfg, int *__restrict__ work_counter)
 {
-    extern __shared__ int xs_smem[];   // per warp: tile_g[32][17], tile_c[32][17], ring[2][RING][32], q[32], base[32]
+    extern __shared__ int xs_smem[];
     __shared__ int s_item;
+    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW, TW = cfg.TW;
+    int *stH = xs_smem;                                  // [NB][CAP][RPI]  h
+    int *stB = stH + NB * CAP * RPI;                     // [NB][CAP][RPI]  s | t << 10 | cy << 20
+    int *meta = stB + NB * CAP * RPI;                    // [NB][RPI]
+    int *tiles = meta + NB * RPI;                        // [NB][2][RPI][TW + 1]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int *wsm = xs_smem + wid * XS_SMEM_INTS_PER_WARP;
-    int (*tile_g)[17] = (int (*)[17])wsm;
-    int (*tile_c)[17] = (int (*)[17])(wsm + 32 * 17);
-    auto ring_of = [&](int w) { return xs_smem + w * XS_SMEM_INTS_PER_WARP + XS_TILE_INTS; };
-    auto meta_of = [&](int w) { return xs_smem + w * XS_SMEM_INTS_PER_WARP + XS_TILE_INTS + XS_RING_INTS; };
-    auto scratch_of = [&](int w) { return scratch + (size_t)(blockIdx.x * XB + w) * L * 32 + lane; };
-    auto view_of = [&](int w) {
-        StackView v;
-        v.sh = ring_of(w) + lane; v.sb = v.sh + RING * 32; v.g = scratch_of(w);
-        v.q = meta_of(w)[lane]; v.base = meta_of(w)[32 + lane];
-        return v;
-    };
-    LaneStack st;
-    st.sh = ring_of(wid) + lane; st.sb = st.sh + RING * 32;
-    st.g = scratch_of(wid);
+    const int r = lane % RPI, b = wid * (32 / RPI) + lane / RPI;
     const int X = m.X, Y = m.Y;
-    const int n_items = __ldg(n_slices) * WY;
-    const int chunk = (((X + XB - 1) / XB) + 15) & ~15;   // x range of a warp in the backward pass, multiple of the tile width
+    const int RG = (Y + RPI - 1) / RPI;                  // row groups per slice
+    const int n_items = __ldg(n_slices) * RG;
+    int *myH = stH + (size_t)b * CAP * RPI + r, *myB = stB + (size_t)b * CAP * RPI + r;
+    int *tile_g = tiles + (size_t)b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);
+    auto M = [&](int k) -> int & { return meta[k * RPI + r]; };
+    auto entH = [&](int k, int i) { return stH[((size_t)k * CAP + i) * RPI + r]; };
+    auto entB = [&](int k, int i) { return stB[((size_t)k * CAP + i) * RPI + r]; };
     for (;;) {
-        __syncthreads();   // the previous item's stacks are no longer read
+        __syncthreads();   // the previous item's stacks and tiles are no longer read
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
         __syncthreads();
         const int item = s_item;
         if (item >= n_items) break;
-        const int zi = item / WY, wy = item - zi * WY;
+        const int zi = item / RG, rg = item - zi * RG;
         const int z = __ldg(&slice_list[zi]);
-        const int y = wy * 32 + lane;
+        const int y = rg * RPI + r;
+        const int wy = y >> 5, p = y & 31;               // ytab word and bit of this row
         const unsigned long long *trow = ytab + ((size_t)z * WY + wy) * X;
         const int *cols = col_list + (size_t)z * X;
         const int nc = __ldg(&n_cols[z]);
-        // ---- forward pass over this warp's band of the real columns
-        const int jb = (int)((long long)nc * wid / XB), je = (int)((long long)nc * (wid + 1) / XB);
-        int q = -1;
-        Top top{0, 0, 0, 0};
-        st.base = 0;
-        const uint32_t lomask = 0xffffffffu >> (31 - lane);
-        for (int j0 = jb; j0 < je; j0 += 4) {
-            // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
-            int uu[4], gg[4], cc[4];
+        // ---- 1. forward pass over this band's real columns
+        {
+            const int jb = (int)((long long)nc * b / NB), je = (int)((long long)nc * (b + 1) / NB);
+            int q = -1;
+            int ts = 0, tt = 0, th = 0;                    // top of the stack (s, t, h) in registers
+            const uint32_t lomask = 0xffffffffu >> (31 - p);
+            for (int j0 = jb; j0 < je; j0 += 4) {
+                // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
+                int uu[4], gg[4], cc[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int j = min(j0 + k, je - 1);
-                int u = __ldg(&cols[j]);
-                unsigned long long e = __ldg(&trow[u]);
-                uint32_t w = (uint32_t)e;
-                int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
-                uint32_t mlo = w & lomask, mhi = w >> lane;
-                int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
-                int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
-                int g1, cy;
-                if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
-                else { g1 = y - lo; cy = lo; }                                          // a real column always has lo or hi
-                uu[k] = u; gg[k] = g1 * g1; cc[k] = cy;
+                for (int k = 0; k < 4; k++) {
+                    int j = min(j0 + k, je - 1);
+                    int u = __ldg(&cols[j]);
+                    unsigned long long e = __ldg(&trow[u]);
+                    uint32_t w = (uint32_t)e;
+                    int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
+                    uint32_t mlo = w & lomask, mhi = w >> p;
+                    int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
+                    int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
+                    int g1, cy;
+                    if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
+                    else { g1 = y - lo; cy = lo; }                                          // a real column always has lo or hi
+                    uu[k] = u; gg[k] = g1 * g1; cc[k] = cy;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (j0 + k >= je) break;
+                    const int u = uu[k], h_u = gg[k];
+                    // EDTphase2 forward loop (local_edt_core.h:93-115)
+                    while (q >= 0) {
+                        int a = tt - ts, c = tt - u;
+                        if (a * a + th > c * c + h_u) {
+                            q--;
+                            if (q >= 0) { int bb = myB[q * RPI]; th = myH[q * RPI]; ts = bb & 0x3ff; tt = (bb >> 10) & 0x3ff; }
+                        } else break;
+                    }
+                    int w = 0;
+                    if (q >= 0) w = 1 + floor_div(u * u - ts * ts + h_u - th, 2 * (u - ts));
+                    if (w < X) {
+                        q++;
+                        ts = u; tt = w; th = h_u;
+                        myH[q * RPI] = h_u;
+                        myB[q * RPI] = u | (w << 10) | (cc[k] << 20);
+                    }
+                }
             }
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (j0 + k < je) envelope_push(uu[k], gg[k], cc[k], X, q, top, st);
+            M(b) = xs_meta_pack(0, q + 1, 0);
         }
-        meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
-        // ---- merge the band envelopes pairwise: (0 <- 1), (2 <- 3), ... then (0 <- 2), (4 <- 6), ... until warp 0 holds the row's
-#pragma unroll
-        for (int stride = 1; stride < XB; stride <<= 1) {
+        // ---- 2. pairwise merges: (0 <- 1), (2 <- 3), ... then (0..1 <- 2..3), ... until the row's envelope is described
+        for (int stride = 1; stride < NB; stride <<= 1) {
             __syncthreads();
-            if ((wid & (2 * stride - 1)) == 0 && wid + stride < XB) {
-                merge_into(q, top, st, view_of(wid + stride), X);
-                meta_of(wid)[lane] = q; meta_of(wid)[32 + lane] = st.base;
+            if ((b & (2 * stride - 1)) != 0 || b + stride >= NB) continue;
+            const int l_end = b + stride, r_end = min(b + 2 * stride, NB);
+            int kl = l_end - 1, kr = l_end;
+            int ml = 0, mr = 0;
+            while (kl >= b && (ml = M(kl), XS_HI1(ml) <= XS_LO(ml))) kl--;
+            while (kr < r_end && (mr = M(kr), XS_HI1(mr) <= XS_LO(mr))) kr++;
+            if (kl < b || kr >= r_end) continue;          // one side is empty: the other stands as it is (its first entry starts at 0)
+            int llo = XS_LO(ml), lhi = XS_HI1(ml) - 1, ltf = XS_TF(ml);
+            int rlo = XS_LO(mr), rhi = XS_HI1(mr) - 1;
+            for (;;) {
+                const int lb = entB(kl, lhi), lh = entH(kl, lhi);
+                const int rb = entB(kr, rlo), rh = entH(kr, rlo);
+                const int ls = lb & 0x3ff, lt = (lhi == llo) ? ltf : ((lb >> 10) & 0x3ff);
+                const int rs = rb & 0x3ff;
+                const int a = lt - ls, c = lt - rs;
+                if (a * a + lh > c * c + rh) {            // the left top is dominated from its own start on: pop it
+                    if (lhi > llo) { lhi--; continue; }
+                    M(kl) = xs_meta_pack(0, 0, 0);
+                    kl--;
+                    while (kl >= b && (ml = M(kl), XS_HI1(ml) <= XS_LO(ml))) kl--;
+                    if (kl < b) { M(kr) = xs_meta_pack(rlo, rhi + 1, 0); break; }   // nothing left on the left: starts at 0
+                    llo = XS_LO(ml); lhi = XS_HI1(ml) - 1; ltf = XS_TF(ml);
+                    continue;
+                }
+                const int w = 1 + floor_div(rs * rs - ls * ls + rh - lh, 2 * (rs - ls));
+                // the first entry of the right envelope ends where its successor starts
+                int rend = X;
+                if (rlo < rhi) rend = (entB(kr, rlo + 1) >> 10) & 0x3ff;
+                else {
+                    int kn = kr + 1, mn = 0;
+                    while (kn < r_end && (mn = M(kn), XS_HI1(mn) <= XS_LO(mn))) kn++;
+                    if (kn < r_end) rend = XS_TF(mn);
+                }
+                if (w >= rend) {                          // squeezed out between the left top and its own successor: drop it
+                    if (rlo < rhi) { rlo++; continue; }
+                    M(kr) = xs_meta_pack(0, 0, 0);
+                    kr++;
+                    while (kr < r_end && (mr = M(kr), XS_HI1(mr) <= XS_LO(mr))) kr++;
+                    if (kr >= r_end) { M(kl) = xs_meta_pack(llo, lhi + 1, ltf); break; }
+                    rlo = XS_LO(mr); rhi = XS_HI1(mr) - 1;
+                    continue;
+                }
+                M(kl) = xs_meta_pack(llo, lhi + 1, ltf);
+                M(kr) = xs_meta_pack(rlo, rhi + 1, w);
+                break;
             }
         }
         __syncthreads();
-        // ---- EDTphase2 backward loop (local_edt_core.h:116-134) over this warp's x range, emitted through a 32 x 16 tile
-        const int x_lo = wid * chunk, x_hi = min(X, x_lo + chunk) - 1;
-        if (x_lo <= x_hi) {
-            const StackView fin = view_of(0);
-            int qq = fin.q;
-            Top e = fin.read(qq);
-            while (e.t > x_hi) { qq--; e = fin.read(qq); }   // the bottom entry starts at 0, so this ends
-            for (int u = x_hi; u >= x_lo; u--) {
-                int d = u - e.s;
-                tile_g[lane][u & 15] = d * d + e.h;
-                tile_c[lane][u & 15] = e.s | (e.cy << 16);
-                if (u == e.t) {
-                    qq--;
-                    if (qq >= 0) e = fin.read(qq);
+        // ---- 3. backward pass over this band's x range, emitted through a RPI x TW tile
+        {
+            const int x_lo = b * BW, x_hi = min(X, x_lo + BW) - 1;
+            const bool act = x_lo <= x_hi;
+            int k = NB - 1, i = 0, lo = 0, tf = 0, es = 0, eh = 0, ecy = 0, et = 0;
+            auto load_entry = [&]() {
+                const int bb = entB(k, i);
+                eh = entH(k, i); es = bb & 0x3ff; ecy = bb >> 20;
+                et = (i == lo) ? tf : ((bb >> 10) & 0x3ff);
+            };
+            if (act) {
+                int mw = 0;
+                for (; k > 0; k--) { mw = M(k); if (XS_HI1(mw) > XS_LO(mw) && XS_TF(mw) <= x_hi) break; }
+                if (k == 0) mw = M(0);                    // the first non-empty band starts at 0: the scan cannot fall through
+                while (XS_HI1(mw) <= XS_LO(mw)) { k++; mw = M(k); }   // (band 0 itself may be empty)
+                lo = XS_LO(mw); tf = XS_TF(mw);
+                i = XS_HI1(mw) - 1;
+                while (i > lo && ((entB(k, i) >> 10) & 0x3ff) > x_hi) i--;
+                load_entry();
+            }
+            const int grp = lane / RPI * RPI;             // first lane of this band's thread group
+            for (int u = x_lo + BW - 1; u >= x_lo; u--) {
+                if (act && u <= x_hi) {
+                    const int d = u - es;
+                    tile_g[r * (TW + 1) + (u % TW)] = d * d + eh;
+                    tile_c[r * (TW + 1) + (u % TW)] = es | (ecy << 16);
+                    if (u == et && u > 0) {                // step to the previous entry of the composite envelope
+                        if (i > lo) i--;
+                        else {
+                            int mw;
+                            do { k--; mw = M(k); } while (XS_HI1(mw) <= XS_LO(mw));
+                            lo = XS_LO(mw); tf = XS_TF(mw); i = XS_HI1(mw) - 1;
+                        }
+                        load_entry();
+                    }
                 }
-                if ((u & 15) == 0) {
+                if ((u % TW) == 0) {
                     __syncwarp();
-                    const int col = lane & 15, r0 = lane >> 4;
-                    const int xx = u + col;
-                    int32_t *pg = g2 + ((size_t)z * Y + wy * 32 + r0) * X + xx;
-                    int32_t *pc = cxy + ((size_t)z * Y + wy * 32 + r0) * X + xx;
+                    if (act) {
+                        const int col = r % TW, r0 = r / TW;
+                        const int xx = u + col;
 #pragma unroll 4
-                    for (int i = 0; i < 16; i++) {
-                        int r = 2 * i + r0;
-                        if (wy * 32 + r < Y && xx < X) {
-                            pg[(size_t)2 * i * X] = tile_g[r][col];
-                            pc[(size_t)2 * i * X] = tile_c[r][col];
+                        for (int rr = r0; rr < RPI; rr += RPI / TW) {
+                            const int yy = rg * RPI + rr;
+                            if (yy < Y && xx < X) {
+                                const size_t o = ((size_t)z * Y + yy) * X + xx;
+                                g2[o] = tile_g[rr * (TW + 1) + col];
+                                cxy[o] = tile_c[rr * (TW + 1) + col];
+                            }
                         }
                     }
                     __syncwarp();
                 }
             }
+            (void)grp;
         }
     }
 }
@@ -455,16 +521,44 @@ int gie_edt_prepare(gie_locmap *lm)
     int need = (n_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (need < ctas) ctas = need;   // small volumes: no idle persistent CTAs
     lm->edt_ctas = ctas;
-    // x sweep: one CTA of XB warps per (slice, 32 rows) item, as many as can be resident
-    int xs_per_sm = 1;
-    GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep, XB * 32, XS_SMEM_BYTES));
-    if (xs_per_sm < 1) xs_per_sm = 1;
-    lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * WY);
-    lm->stack_scratch_entries = (size_t)std::max(ctas * WARPS_PER_CTA, lm->xs_ctas * XB) * L * 32;
+    // x sweep: one CTA per (slice, RPI rows) item; bands of ~32 columns, one band per warp (RPI = 32) or two (RPI = 16, the
+    // only shape whose stacks fit shared memory for X > 512).  GIE_XS_RPI overrides the choice (measurement switch).
+    {
+        int rpi = m.X <= 512 ? 32 : 16;
+        if (getenv("GIE_XS_RPI")) { int v = atoi(getenv("GIE_XS_RPI")); if (v == 16 || (v == 32 && m.X <= 512)) rpi = v; }
+        const int per_warp = 32 / rpi;
+        int nwarps = std::min(16, (m.X + 31) / 32);
+        XsLaunch &x = lm->xs;
+        x.rpi = rpi; x.threads = nwarps * 32;
+        x.NB = nwarps * per_warp;
+        x.TW = rpi == 32 ? 16 : 8;
+        x.CAP = (m.X + x.NB - 1) / x.NB;
+        x.BW = ((m.X + x.NB - 1) / x.NB + x.TW - 1) / x.TW * x.TW;
+        x.smem = (size_t)(2 * x.NB * x.CAP * rpi + x.NB * rpi + x.NB * 2 * rpi * (x.TW + 1)) * 4;
+        if (rpi == 32) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
+        else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
+        int xs_per_sm = 1;
+        if (rpi == 32) GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<32>, x.threads, x.smem));
+        else GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<16>, x.threads, x.smem));
+        if (xs_per_sm < 1) { gie_set_error("x sweep does not fit on an SM"); return GIE_ERR_CUDA; }
+        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.Y + rpi - 1) / rpi));
+    }
+    lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
     GIE_CUDA_CHECK(cudaMalloc(&lm->stack_scratch, lm->stack_scratch_entries * 8));
     GIE_CUDA_CHECK(cudaMalloc(&lm->work_counters, 4 * sizeof(int)));
-    GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep, cudaFuncAttributeMaxDynamicSharedMemorySize, XS_SMEM_BYTES));
     return GIE_OK;
+}
+
+static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, int *n_slices)
+{
+    const XsLaunch &x = lm->xs;
+    const XsCfg cfg{ x.NB, x.CAP, x.BW, x.TW };
+    if (x.rpi == 32)
+        k_edt_xsweep<32><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0);
+    else
+        k_edt_xsweep<16><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
+                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0);
 }
 
 // The two halves of the batch EDT as separate launches, for the multi-GPU path (gie-mapping_b200/sharded.py): the y and x
@@ -479,8 +573,7 @@ int gie_launch_edt_xy(gie_locmap *lm)
     launch_ybits(lm, WY);
     k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
-    k_edt_xsweep<<<lm->xs_ctas, XB * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                              lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
+    launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
     lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -516,8 +609,7 @@ int gie_launch_batch_edt(gie_locmap *lm)
     }
     {
         StageTimer t(lm, GIE_ST_EDT_X);
-        k_edt_xsweep<<<lm->xs_ctas, XB * 32, XS_SMEM_BYTES, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                  lm->g2, lm->cxy, (uint2 *)lm->stack_scratch, L, lm->work_counters + 0);
+        launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_Z);

@@ -4,6 +4,8 @@
 #include "../../include/gie_b200.h"
 #include <string>
 
+struct XsLaunch { int rpi = 32, threads = 0, NB = 0, CAP = 0, BW = 0, TW = 0; size_t smem = 0; };   // x-sweep launch shape (edt.cu)
+
 struct gie_locmap {
     LocDev d{};                 // device view, passed by value to kernels (as the reference passes LocMap)
     cudaStream_t stream = nullptr;
@@ -19,7 +21,8 @@ struct gie_locmap {
     unsigned long long *stack_scratch = nullptr;
     size_t stack_scratch_entries = 0;
     int edt_ctas = 0;                     // persistent grid of the z sweep
-    int xs_ctas = 0;                      // persistent grid of the x sweep (4 warps per CTA)
+    int xs_ctas = 0;                      // persistent grid of the x sweep
+    XsLaunch xs;
     int *work_counters = nullptr;         // device: [4]
     // staging for *_host entry points
     float *stage_dev = nullptr;

@@ -363,8 +363,9 @@ def _golden_cases():
 def test_cuda_engine_vs_reference_golden(gie, path):
     """The CUDA engine directly against the fixtures produced by the reference's OWN CUDA sources on a B200
     (tests/golden/*.npz, oracle/gen_golden.py): bit-exact occupancy, batch dist_sq and committed (dist, coc) on every frame
-    before the first wavefront activity; afterwards the reference is schedule dependent, so >= 95 % identical
-    voxels with the differing ones in the majority closer here — the same bar the oracle is held to."""
+    before the first wavefront activity; afterwards equal-distance offers are resolved by arrival order there and by the
+    smaller coc id here, so >= 99.9 % identical distances — the same bar the oracle is held to; the
+    ground-truth accounting of the differing voxels is in test_engine_pinned_against_reference_fixture."""
     g = np.load(path)
     cfg = gie.scenes.small_config(str(g["cfg_name"]), tuple(int(v) for v in g["size"]), cutoff_grids_sq=int(g["cutoff"]))
     frames = gie.scenes.make_frames(cfg, int(g["nframes"]), dynamic=bool(g["dynamic"]))
