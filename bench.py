@@ -44,17 +44,44 @@ def load_pkg():
     return mod
 
 
-# Algorithmic bytes per voxel (SURVEY §8d / DESIGN.md §3): what a dense volume with every voxel known would have to move.
-# The batch-DT figure is the packed-intermediate 41 B/voxel of SURVEY §8d for the three sweeps together.  The engine skips
-# UNKNOWN voxels and obstacle-free slices, so measured DRAM traffic (ncu, profiles/) is lower than these figures and
-# "achieved" can exceed the copy peak; both are reported.
-ALGO_BYTES = {
-    "hash_merge": 15.0,     # count R4+W4, inst R1+W1, glb_type W1, voxel occ/type R2+W2
-    "batch_dt": 41.0,       # P1 1R+8W, P2 8R+8W, P3 8R+8W   (edt_pack + edt_x + edt_z)
-}
-# mark / frontiers / commit walk only the allocated blocks (a few % of the volume): no per-voxel figure, see ncu traffic
-OTHER_STAGES = ("ogm", "mark_frontier", "waves", "commit")
+# Algorithmic bytes of the batch DT.  Two figures are reported and labelled:
+#   * `achieved` uses the bytes the three sweeps of THIS engine have to move for the frame at hand — a function of s, the
+#     fraction of z-slices that hold an obstacle (slices without one are never written by the x sweep nor read by the z sweep):
+#       y pass : 1 R (glb_type) + 0.25 W (bit words) + 0.25 R + 0.25 W (links)
+#       x sweep: 0.25 s R (bit words) + 8 s W (g2, cxy)
+#       z sweep: 8 s R + 8 W (aux, coc_aux)                                     => 9.75 + 16.25 s  bytes per voxel
+#     (ncu's dram__bytes for the same launches is `traffic`; the two agree within a few percent, profiles/README.md);
+#   * `survey_41B_figure` is SURVEY §8d's packed-intermediate 41 B/voxel (P1 1R+8W, P2 8R+8W, P3 8R+8W), the traffic of a
+#     design that materialises every pass for every voxel; it exceeds what is moved here and is NOT used for `frac`.
+SURVEY_BATCH_DT_BYTES = 41.0
 BATCH_DT_STAGES = ("edt_pack", "edt_x", "edt_z")
+OTHER_STAGES = ("ogm", "hash_merge", "mark_frontier", "waves", "commit")
+
+
+def batch_dt_bytes_per_voxel(s):
+    return 9.75 + 16.25 * s
+
+
+def workload_string(cfg, frames):
+    """One description of the workload, identical in both arms (the driver compares the strings)."""
+    X, Y, Z = cfg["local_size"]
+    key = {"pointcloud": "points", "scan2d": "scan", "vlp16": "ranges", "depth": "depth"}[cfg["sensor"]]
+    n = int(np.mean([np.asarray(f[key]).size for f in frames]))
+    per = f"{n // 3} points/frame" if cfg["sensor"] == "pointcloud" else f"{n} range values/frame"
+    return (f"{cfg['name']}: {X}x{Y}x{Z} @ {cfg['voxel_width']} m, {cfg['sensor']} {per}, cutoff_grids_sq={cfg['cutoff_grids_sq']}, "
+            f"fast_mode={cfg['fast_mode']}")
+
+
+def host_info():
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model}
 
 
 class ClockSampler(threading.Thread):
@@ -109,25 +136,32 @@ def measured_peak():
 
 
 def cpu_baseline(gie, cfg, frames):
-    """C oracle on a bounded sample: same sensor frames, local volume cropped to 256^3 (1/8 of the voxels), 2 frames."""
+    """The C oracle (a port: the reference has no CPU implementation of this path) at the FULL size of the workload, on a
+    bounded sample of its frames: single-threaded, and with the batch EDT's column loops spread over all host cores
+    (pthreads; ray cast, hash merge and wavefronts stay serial).  `value` is the all-core figure."""
     from oracle import oracle_py
-    sub = dict(cfg)
+    info = host_info()
+    out = {"unit": "frames/s", "kind": "port", **info}
+    runs = {}
+    for label, threads, n in (("single_thread", 1, 2), ("all_cores", info["nproc"] or 1, 3)):
+        oracle_py.set_threads(threads)
+        om = oracle_py.OracleMapper(cfg)
+        n = min(n, len(frames))
+        t0 = time.perf_counter()
+        for f in frames[:n]:
+            om.publishMap(f)
+        dt = time.perf_counter() - t0
+        om.close()
+        runs[label] = {"value": n / dt, "frames": n, "seconds": dt, "threads": threads}
+    oracle_py.set_threads(1)
     X, Y, Z = cfg["local_size"]
-    sub["local_size"] = (min(X, 256), min(Y, 256), min(Z, 256))
-    om = oracle_py.OracleMapper(sub)
-    n = min(10, len(frames))
-    t0 = time.perf_counter()
-    for f in frames[:n]:
-        om.publishMap(f)
-    dt = time.perf_counter() - t0
-    om.close()
-    vox = sub["local_size"][0] * sub["local_size"][1] * sub["local_size"][2]
-    full = X * Y * Z
-    fps_equiv = (vox * n / dt) / full
-    return {"value": fps_equiv, "unit": "frames/s", "cores": 1, "kind": "port",
-            "sample": f"{n} frames of the {cfg['name']} sensor stream on a {sub['local_size']} crop of the local volume "
-                      f"({dt:.1f} s CPU); frames/s scaled by voxel count to {cfg['local_size']}",
-            "mvoxels_per_s": vox * n / dt / 1e6}
+    out.update({"value": runs["all_cores"]["value"], "cores": runs["all_cores"]["threads"],
+                "single_thread": runs["single_thread"], "all_cores": runs["all_cores"],
+                "mvoxels_per_s": runs["all_cores"]["value"] * X * Y * Z / 1e6,
+                "sample": f"the first {runs['single_thread']['frames']} (1 thread, {runs['single_thread']['seconds']:.1f} s) and "
+                          f"{runs['all_cores']['frames']} ({runs['all_cores']['threads']} threads, {runs['all_cores']['seconds']:.1f} s) frames of "
+                          f"the {cfg['name']} stream at the full {X}x{Y}x{Z} volume"})
+    return out
 
 
 def batch_dt_dense_case(gie, cfg, stream):
@@ -156,8 +190,11 @@ def batch_dt_dense_case(gie, cfg, stream):
         lm.close()
     nvox = X * Y * Z
     peak, _ = measured_peak()
-    ach = ALGO_BYTES["batch_dt"] * nvox / (ms * 1e-3) / 1e9
-    return {"workload": f"{X}x{Y}x{Z}, random 0.2 % occupancy in every slice", "ms": ms, "achieved": ach, "frac": ach / peak}
+    bpv = batch_dt_bytes_per_voxel(1.0)
+    ach = bpv * nvox / (ms * 1e-3) / 1e9
+    return {"workload": f"{X}x{Y}x{Z}, random 0.2 % occupancy in every slice (s = 1: nothing to skip)", "ms": ms,
+            "bytes_per_voxel": bpv, "achieved": ach, "frac": ach / peak,
+            "survey_41B_figure": {"achieved": SURVEY_BATCH_DT_BYTES * nvox / (ms * 1e-3) / 1e9}}
 
 
 def cpp_host_leg(gie, cfg, frames, warmup):
@@ -226,7 +263,7 @@ def run_reference(args, gie, cfg, frames):
         return None
     line = {"impl": "reference", "metric": "EDT+OGM frames/sec", "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f32",
-            "data": "synthetic"}
+            "data": "synthetic", "config": {"workload": workload_string(cfg, frames)}}
     X, Y, Z = cfg["local_size"]
     nvox = X * Y * Z
     t = None
@@ -237,21 +274,27 @@ def run_reference(args, gie, cfg, frames):
             line["reference_driver_error"] = repr(e)[:200]
     if t:
         t = t[args.warmup:]
-        ms = float(np.mean([a + b for a, b in t]))
+        per_frame = np.array([a + b for a, b in t])
+        # the reference's OGM half allocates and sorts 134 M keys per frame: its frame time has a long tail and moves between
+        # boxes, so the MEDIAN frame is reported (mean, quartiles and both halves are kept beside it)
+        ms = float(np.median(per_frame))
         fps = 1000.0 / ms
         pts_bytes = int(np.mean([f[ref_io.PAYLOAD_KEY[cfg["sensor"]]].nbytes for f in frames]))
-        line.update({"value": fps, "ms_per_step": ms, "mvoxels_per_s": fps * nvox / 1e6,
-                     "stage_ms": {"ogm_half": float(np.mean([a for a, _ in t])), "edt_half": float(np.mean([b for _, b in t]))},
-                     "config": {"workload": f"{cfg['name']}: {X}x{Y}x{Z} @ {cfg['voxel_width']} m, {cfg['sensor']}, "
-                                            f"cutoff_grids_sq={cfg['cutoff_grids_sq']}, fast_mode={cfg['fast_mode']}"},
-                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference",
+        q = lambda v, p: float(np.percentile(v, p))
+        ogm, edt = np.array([a for a, _ in t]), np.array([b for _, b in t])
+        line.update({"value": fps, "ms_per_step": ms, "mvoxels_per_s": fps * nvox / 1e6, "statistic": f"median of {len(t)} frames",
+                     "spread_ms": {"mean": float(per_frame.mean()), "p25": q(per_frame, 25), "p75": q(per_frame, 75), "min": float(per_frame.min()),
+                                   "max": float(per_frame.max())},
+                     "stage_ms": {"ogm_half": {"median": float(np.median(ogm)), "p25": q(ogm, 25), "p75": q(ogm, 75)},
+                                  "edt_half": {"median": float(np.median(edt)), "p25": q(edt, 25), "p75": q(edt, 75)}},
+                     "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": 1, "kind": "reference", **host_info(),
                                       "sample": "the reference's own CUDA sources (unmodified, Release flags, cuTT replaced by a gather "
                                                 "shim) recompiled for sm_100a and run on the GPU; it has no CPU implementation; "
                                                 "host-timed per frame with cudaDeviceSynchronize as the reference does"},
                      "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": pts_bytes, "d2h_bytes_per_step": 0}})
     else:
         cb = cpu_baseline(gie, cfg, frames)
-        line.update({"value": cb["value"], "ms_per_step": 1000.0 / cb["value"], "config": {"workload": cfg["name"]},
+        line.update({"value": cb["value"], "ms_per_step": 1000.0 / cb["value"],
                      "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     print(json.dumps(line), flush=True)
     return line
@@ -340,14 +383,6 @@ def main():
     sampler.start()
     time.sleep(0.3)
     ms_dev, launches, mp = run_pass(True)
-    # stage profile on the same map, continuing the stream of frames (not part of the timed region)
-    mp.loc_map.profile_enable(True)
-    prof = {}
-    reps = min(10, args.steps)
-    for k in range(nframes - reps, nframes):
-        mp.publishMap(frames[k], device_input=dev_in[k].data_ptr())
-        for name, v in mp.loc_map.profile_last().items():
-            prof[name] = prof.get(name, 0.0) + v / reps
     wave_stats = mp.hash_map.wave_stats()
     nblocks = mp.hash_map.num_blocks()
     mp.close()
@@ -355,54 +390,77 @@ def main():
     mp2.close()
     sampler.stop()
     clocks = sampler.summary()
+    # Stage profile: a THIRD pass over the very same frames with CUDA events around every stage (the events themselves cost a
+    # little, so this pass is not the timed one).  frame - sum(stages) is then the time spent outside kernels on these frames.
+    mp3 = gie.Mapper(cfg)
+    mp3.loc_map.set_stream(stream.cuda_stream)
+    for k in range(args.warmup):
+        mp3.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+    mp3.loc_map.profile_enable(True)
+    prof, slice_frac = {}, 0.0
+    for k in range(args.warmup, nframes):
+        mp3.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+        for name, v in mp3.loc_map.profile_last().items():
+            prof[name] = prof.get(name, 0.0) + v / args.steps
+        slice_frac += float((mp3.loc_map.edt_slice_columns() > 0).mean()) / args.steps
+    mp3.close()
 
     X, Y, Z = cfg["local_size"]
     nvox = X * Y * Z
     fps = world * 1000.0 / ms_dev
     fps_e2e = world * 1000.0 / ms_e2e
     peak, peak_src = measured_peak()
+    stage_sum = sum(prof.values())
     prof["batch_dt"] = sum(prof.get(k, 0.0) for k in BATCH_DT_STAGES)
     dense = batch_dt_dense_case(gie, cfg, stream) if (rank == 0 and not args.no_dense_case) else None
 
-    def gbs(name, ms):
-        return ALGO_BYTES[name] * nvox / (ms * 1e-3) / 1e9 if ms and ms > 0 else None
-
-    # The roofline object is reported for the batch-DT sweep group (EDT_OCC::batchEDTUpdate), the kernel north_star grades;
-    # the longest single stage of the frame is named in `longest_stage` (the wavefront kernel is latency-bound: no byte figure).
-    achieved = gbs("batch_dt", prof["batch_dt"]) or 0.0
-    traffic_file = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    # The roofline object is reported for the batch-DT sweep group (EDT_OCC::batchEDTUpdate), the kernel north_star grades.
+    bpv = batch_dt_bytes_per_voxel(slice_frac)
+    achieved = bpv * nvox / (prof["batch_dt"] * 1e-3) / 1e9 if prof["batch_dt"] > 0 else 0.0
     traffic = {}
-    if os.path.exists(traffic_file):
-        try:
-            traffic = json.load(open(traffic_file))
-        except Exception:
-            traffic = {}
-    roofline = {"bound": "hbm", "kernel": "batch_dt = k_edt_ycols + k_edt_slices + k_edt_xsweep + k_edt_zsweep (EDT_OCC::batchEDTUpdate)",
+    for tf in ("traffic_r02.json", "traffic_r01.json"):
+        tp = os.path.join(ROOT, "profiles", tf)
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp))
+                traffic["_file"] = tf
+                break
+            except Exception:
+                traffic = {}
+
+    def per_kernel(k):
+        d = {"ms": prof.get(k, 0.0), "ncu_dram_bytes": traffic.get(k)}
+        if traffic.get(k) and prof.get(k, 0.0) > 0:
+            d["dram_gbs"] = traffic[k] / (prof[k] * 1e-3) / 1e9      # measured bytes of one ncu capture / live event time
+        return d
+
+    roofline = {"bound": "hbm", "kernel": "batch_dt = k_edt_ybits + k_edt_ycols + k_edt_slices + k_edt_xsweep + k_edt_zsweep (EDT_OCC::batchEDTUpdate)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get("batch_dt"),
-                "algorithmic_bytes_per_voxel": ALGO_BYTES["batch_dt"], "algorithmic_bytes_per_launch": ALGO_BYTES["batch_dt"] * nvox,
+                "frac": achieved / peak, "traffic": traffic.get("batch_dt"), "traffic_source": traffic.get("_file"),
+                "algorithmic_bytes_per_voxel": bpv, "algorithmic_bytes_per_launch": bpv * nvox,
+                "bytes_formula": "9.75 + 16.25 s B/voxel, s = fraction of z-slices holding an obstacle (bytes this engine's sweeps must move)",
+                "obstacle_slice_fraction": slice_frac,
+                "survey_41B_figure": {"bytes_per_voxel": SURVEY_BATCH_DT_BYTES, "achieved": SURVEY_BATCH_DT_BYTES * nvox / (prof["batch_dt"] * 1e-3) / 1e9
+                                      if prof["batch_dt"] > 0 else None,
+                                      "note": "traffic of a design that materialises all three passes for every voxel; larger than what is moved here, not used for frac"},
                 "kernel_ms": prof["batch_dt"], "kernel_ms_parts": {k: prof.get(k, 0.0) for k in BATCH_DT_STAGES},
-                "note": "live CUDA-event time of the three sweep kernels on the engine stream, mean of the last "
-                        f"{reps} frames; the scene has obstacles in a minority of z-slices, which the sweeps skip",
+                "note": f"live CUDA-event time of the sweep kernels on the engine stream, mean over the {args.steps} timed frames (profiled pass)",
                 "dense_case": dense,
-                "longest_stage": max((k for k in prof if k not in BATCH_DT_STAGES), key=lambda k: prof[k]),
-                "per_kernel": {**{k: {"ms": prof.get(k, 0.0), "algorithmic_bytes_per_voxel": ALGO_BYTES[k], "achieved_gbs": gbs(k, prof.get(k, 0.0)),
-                                      "ncu_dram_bytes": traffic.get(k)} for k in ALGO_BYTES},
-                               **{k: {"ms": prof.get(k, 0.0), "ncu_dram_bytes": traffic.get(k)} for k in OTHER_STAGES}}}
+                "longest_stage": max((k for k in prof if k not in BATCH_DT_STAGES and k != "batch_dt"), key=lambda k: prof[k]),
+                "per_kernel": {k: per_kernel(k) for k in BATCH_DT_STAGES + OTHER_STAGES}}
     line = {"metric": "EDT+OGM frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32+f32", "data": "synthetic",
-            "config": {"workload": f"{cfg['name']}: {X}x{Y}x{Z} @ {cfg['voxel_width']} m, {cfg['sensor']} "
-                                   f"{int(np.mean([h.numel() for h in host_in])) // 3 if cfg['sensor'] == 'pointcloud' else host_in[0].numel()} "
-                                   f"values/frame, cutoff_grids_sq={cfg['cutoff_grids_sq']}, fast_mode={cfg['fast_mode']}",
+            "config": {"workload": workload_string(cfg, frames),
                        "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas of the per-frame path (one map per GPU, no "
                                                                   "data-path collective); the sharded batch EDT is reported separately",
-                       "l2": "per-frame working set (>= 3 GB) exceeds the 126 MB L2; no explicit flush"},
+                       "l2": "per-frame working set (>= 1.5 GB) exceeds the 126 MB L2; no explicit flush"},
             "mvoxels_per_s": fps * nvox / 1e6,
             "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(np.mean([h.numel() * 4 for h in host_in])) + 28, "d2h_bytes_per_step": 4 + 64},
             "gpu_launches": int(launches),
-            "stage_ms": prof, "wave_stats": wave_stats, "blocks": nblocks,
+            "stage_ms": prof, "outside_kernels_ms": ms_dev - stage_sum,
+            "wave_stats": wave_stats, "blocks": nblocks,
             "roofline": roofline, "clocks": clocks}
     if not args.no_sharded_edt and (world > 1 or args.sharded_edt):
         line["sharded_batch_edt"] = sharded_edt_leg(world, rank)

@@ -188,52 +188,174 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
     }
 }
 
-// ---- x sweep (EDTphase2, local_edt_core.h:84-135) ---------------------------------------------------------------------
-// Work item = (obstacle-bearing slice z, RPI consecutive rows y); thread = (band b, row r).  The real columns of the slice
-// are cut into NB bands of at most CAP candidates.
-//   1. forward: every (band, row) thread builds the lower envelope of ITS band with the reference's sequential push
-//      (envelope_step), the whole stack in shared memory ([band][entry][row], conflict free).
+// ---- banded envelope machinery shared by the x sweep and the dense z sweep ---------------------------------------------
+// The candidates of one scan line (real columns of a row / real slices of a z column) are cut into NB bands of at most CAP
+// candidates; thread = (band b, line r), R lines per work item.
+//   1. forward: every (band, line) thread builds the lower envelope of ITS band with the reference's sequential push, the
+//      whole stack in shared memory ([band][entry][line], conflict free).
 //   2. merge: parabolas of equal curvature cross exactly once, so the envelope of (left bands) U (right bands) is a prefix
 //      of the left envelope followed by a suffix of the right one.  Re-pushing the right envelope onto the left with the
 //      sequential algorithm would pop some top entries of the left, drop some first entries of the right, and then copy the
 //      rest unchanged — so only the cut is searched (a two-pointer loop of typically 1-3 steps) and recorded per band as
 //      (lo, hi, tfirst): the surviving entry range of the band's stack and the start of its first survivor.  Bands are merged
 //      pairwise in a tree (log2 NB rounds).  Same comparisons, same integer divisions, same tie behaviour as the push loop.
-//   3. backward (local_edt_core.h:116-134): x is cut into NB ranges; every (range, row) thread finds the entry that covers
-//      the end of its range in the composite envelope and walks down, emitting through a [RPI][TW] shared-memory tile so that
-//      global stores run along x.  This is the in-kernel transpose that replaces cuTT's {1,0,2} permutation and its inverse.
-// A serial scan of a 512-wide row is ~1000 dependent steps; here the dependent chain of an item is CAP + BW (+ merges)
-// ~ 70 steps, and a slice with few obstacle columns still keeps NB x 32 threads busy.
-struct XsCfg { int NB, CAP, BW, TW; };   // bands, stack capacity per band, x range per band (multiple of TW), tile width
+//   3. backward: the scan line is cut into NB ranges; every (range, line) thread finds the entry that covers the end of its
+//      range in the composite envelope (EnvCursor) and walks down.
+// A serial scan of a 512-long line is ~1000 dependent steps; here the dependent chain of an item is CAP + range (+ merges)
+// ~ 70 steps, and a line with few candidates still keeps NB x 32 threads busy.
+struct BandCfg { int NB, CAP, BW; };   // bands, stack capacity per band, output range per band
 
-__device__ __forceinline__ int xs_meta_pack(int lo, int hi1, int tf) { return lo | (hi1 << 8) | (tf << 16); }
-#define XS_LO(mw) ((mw) & 0xff)
-#define XS_HI1(mw) (((mw) >> 8) & 0xff)      // hi + 1; the range [lo, hi] is empty when hi1 <= lo
-#define XS_TF(mw) ((mw) >> 16)
+__device__ __forceinline__ int bd_meta_pack(int lo, int hi1, int tf) { return lo | (hi1 << 8) | (tf << 16); }
+#define BD_LO(mw) ((mw) & 0xff)
+#define BD_HI1(mw) (((mw) >> 8) & 0xff)      // hi + 1; the range [lo, hi] is empty when hi1 <= lo
+#define BD_TF(mw) ((mw) >> 16)
+#define BD_EMPTY(mw) (BD_HI1(mw) <= BD_LO(mw))
 
+// Shared-memory view of the stacks of one work item for the thread's line r.  Entry = (h, s | t << 10 [| cy << 20]).
+template <int R>
+struct BandStacks {
+    int *stH, *stB, *meta;
+    int CAP, r;
+    __device__ __forceinline__ int &M(int k) const { return meta[k * R + r]; }
+    __device__ __forceinline__ int H(int k, int i) const { return stH[(k * CAP + i) * R + r]; }
+    __device__ __forceinline__ int B(int k, int i) const { return stB[(k * CAP + i) * R + r]; }
+};
+
+// one push of the sequential algorithm (EDTphase2/3 forward loops, local_edt_core.h:93-115 / :146-168) onto the stack of band
+// `b`; (ts, tt, th) = top entry in registers, q = its index.  `extra` is or-ed into the packed word (the x sweep keeps cy there).
+template <int R>
+__device__ __forceinline__ void band_push(const BandStacks<R> &S, int b, int u, int h_u, int extra, int L, int &q, int &ts, int &tt, int &th)
+{
+    int *myH = S.stH + (size_t)b * S.CAP * R + S.r, *myB = S.stB + (size_t)b * S.CAP * R + S.r;
+    while (q >= 0) {
+        const int a = tt - ts, c = tt - u;
+        if (a * a + th > c * c + h_u) {
+            q--;
+            if (q >= 0) { const int bb = myB[q * R]; th = myH[q * R]; ts = bb & 0x3ff; tt = (bb >> 10) & 0x3ff; }
+        } else break;
+    }
+    int w = 0;
+    if (q >= 0) w = 1 + floor_div(u * u - ts * ts + h_u - th, 2 * (u - ts));
+    if (w < L) {
+        q++;
+        ts = u; tt = w; th = h_u;
+        myH[q * R] = h_u;
+        myB[q * R] = u | (w << 10) | extra;
+    }
+}
+
+// merge of the composite envelope of bands [b, b + stride) with that of bands [b + stride, b + 2 stride): see above
+template <int R>
+__device__ __forceinline__ void band_merge(const BandStacks<R> &S, int b, int stride, int NB, int L)
+{
+    const int l_end = b + stride, r_end = min(b + 2 * stride, NB);
+    int kl = l_end - 1, kr = l_end;
+    int ml = 0, mr = 0;
+    while (kl >= b && (ml = S.M(kl), BD_EMPTY(ml))) kl--;
+    while (kr < r_end && (mr = S.M(kr), BD_EMPTY(mr))) kr++;
+    if (kl < b || kr >= r_end) return;            // one side is empty: the other stands as it is (its first entry starts at 0)
+    int llo = BD_LO(ml), lhi = BD_HI1(ml) - 1, ltf = BD_TF(ml);
+    int rlo = BD_LO(mr), rhi = BD_HI1(mr) - 1;
+    for (;;) {
+        const int lb = S.B(kl, lhi), lh = S.H(kl, lhi);
+        const int rb = S.B(kr, rlo), rh = S.H(kr, rlo);
+        const int ls = lb & 0x3ff, lt = (lhi == llo) ? ltf : ((lb >> 10) & 0x3ff);
+        const int rs = rb & 0x3ff;
+        const int a = lt - ls, c = lt - rs;
+        if (a * a + lh > c * c + rh) {            // the left top is dominated from its own start on: pop it
+            if (lhi > llo) { lhi--; continue; }
+            S.M(kl) = bd_meta_pack(0, 0, 0);
+            kl--;
+            while (kl >= b && (ml = S.M(kl), BD_EMPTY(ml))) kl--;
+            if (kl < b) { S.M(kr) = bd_meta_pack(rlo, rhi + 1, 0); return; }   // nothing left on the left: starts at 0
+            llo = BD_LO(ml); lhi = BD_HI1(ml) - 1; ltf = BD_TF(ml);
+            continue;
+        }
+        const int w = 1 + floor_div(rs * rs - ls * ls + rh - lh, 2 * (rs - ls));
+        // the first entry of the right envelope ends where its successor starts
+        int rend = L;
+        if (rlo < rhi) rend = (S.B(kr, rlo + 1) >> 10) & 0x3ff;
+        else {
+            int kn = kr + 1, mn = 0;
+            while (kn < r_end && (mn = S.M(kn), BD_EMPTY(mn))) kn++;
+            if (kn < r_end) rend = BD_TF(mn);
+        }
+        if (w >= rend) {                          // squeezed out between the left top and its own successor: drop it
+            if (rlo < rhi) { rlo++; continue; }
+            S.M(kr) = bd_meta_pack(0, 0, 0);
+            kr++;
+            while (kr < r_end && (mr = S.M(kr), BD_EMPTY(mr))) kr++;
+            if (kr >= r_end) { S.M(kl) = bd_meta_pack(llo, lhi + 1, ltf); return; }
+            rlo = BD_LO(mr); rhi = BD_HI1(mr) - 1;
+            continue;
+        }
+        S.M(kl) = bd_meta_pack(llo, lhi + 1, ltf);
+        S.M(kr) = bd_meta_pack(rlo, rhi + 1, w);
+        return;
+    }
+}
+
+// position in the composite envelope during the backward pass
+template <int R>
+struct EnvCursor {
+    int k, i, lo, tf;        // band, entry, first surviving entry of the band and its start
+    int es, eh, eb, et;      // current entry: site, height, packed word, start
+    __device__ __forceinline__ void load(const BandStacks<R> &S)
+    {
+        eb = S.B(k, i); eh = S.H(k, i);
+        es = eb & 0x3ff;
+        et = (i == lo) ? tf : ((eb >> 10) & 0x3ff);
+    }
+    // the entry that covers position p (the last one whose start is <= p)
+    __device__ __forceinline__ void seek(const BandStacks<R> &S, int NB, int p)
+    {
+        int mw = 0;
+        for (k = NB - 1; k > 0; k--) { mw = S.M(k); if (!BD_EMPTY(mw) && BD_TF(mw) <= p) break; }
+        if (k == 0) mw = S.M(0);                  // the first non-empty band starts at 0: the scan cannot fall through
+        while (BD_EMPTY(mw)) { k++; mw = S.M(k); }   // (band 0 itself may be empty)
+        lo = BD_LO(mw); tf = BD_TF(mw);
+        i = BD_HI1(mw) - 1;
+        while (i > lo && ((S.B(k, i) >> 10) & 0x3ff) > p) i--;
+        load(S);
+    }
+    // step to the previous entry of the composite envelope (the caller guarantees there is one)
+    __device__ __forceinline__ void prev(const BandStacks<R> &S)
+    {
+        if (i > lo) i--;
+        else {
+            int mw;
+            do { k--; mw = S.M(k); } while (BD_EMPTY(mw));
+            lo = BD_LO(mw); tf = BD_TF(mw); i = BD_HI1(mw) - 1;
+        }
+        load(S);
+    }
+};
+
+// ---- x sweep (EDTphase2, local_edt_core.h:84-135) ---------------------------------------------------------------------
+// Work item = (obstacle-bearing slice z, RPI consecutive rows y); thread = (band of real columns, row).  The backward pass
+// emits through a [RPI][TW] shared-memory tile so that global stores run along x: the in-kernel transpose that replaces
+// cuTT's {1,0,2} permutation and its inverse.
 template <int RPI>
 __global__ void __launch_bounds__(512)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
-             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, XsCfg cfg, int *__restrict__ work_counter)
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter)
 {
+    constexpr int TW = RPI == 32 ? 16 : 8;               // tile width: a row segment of 64 / 32 bytes per store
     extern __shared__ int xs_smem[];
     __shared__ int s_item;
-    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW, TW = cfg.TW;
-    int *stH = xs_smem;                                  // [NB][CAP][RPI]  h
-    int *stB = stH + NB * CAP * RPI;                     // [NB][CAP][RPI]  s | t << 10 | cy << 20
-    int *meta = stB + NB * CAP * RPI;                    // [NB][RPI]
-    int *tiles = meta + NB * RPI;                        // [NB][2][RPI][TW + 1]
+    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int r = lane % RPI, b = wid * (32 / RPI) + lane / RPI;
+    BandStacks<RPI> S;
+    S.stH = xs_smem;                                     // [NB][CAP][RPI]  h
+    S.stB = S.stH + NB * CAP * RPI;                      // [NB][CAP][RPI]  s | t << 10 | cy << 20
+    S.meta = S.stB + NB * CAP * RPI;                     // [NB][RPI]
+    S.CAP = CAP; S.r = r;
+    int *tile_g = S.meta + NB * RPI + b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);   // [NB][2][RPI][TW + 1]
     const int X = m.X, Y = m.Y;
     const int RG = (Y + RPI - 1) / RPI;                  // row groups per slice
     const int n_items = __ldg(n_slices) * RG;
-    int *myH = stH + (size_t)b * CAP * RPI + r, *myB = stB + (size_t)b * CAP * RPI + r;
-    int *tile_g = tiles + (size_t)b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);
-    auto M = [&](int k) -> int & { return meta[k * RPI + r]; };
-    auto entH = [&](int k, int i) { return stH[((size_t)k * CAP + i) * RPI + r]; };
-    auto entB = [&](int k, int i) { return stB[((size_t)k * CAP + i) * RPI + r]; };
     for (;;) {
         __syncthreads();   // the previous item's stacks and tiles are no longer read
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
@@ -250,8 +372,7 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
         // ---- 1. forward pass over this band's real columns
         {
             const int jb = (int)((long long)nc * b / NB), je = (int)((long long)nc * (b + 1) / NB);
-            int q = -1;
-            int ts = 0, tt = 0, th = 0;                    // top of the stack (s, t, h) in registers
+            int q = -1, ts = 0, tt = 0, th = 0;
             const uint32_t lomask = 0xffffffffu >> (31 - p);
             for (int j0 = jb; j0 < je; j0 += 4) {
                 // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
@@ -272,135 +393,131 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
                     uu[k] = u; gg[k] = g1 * g1; cc[k] = cy;
                 }
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    if (j0 + k >= je) break;
-                    const int u = uu[k], h_u = gg[k];
-                    // EDTphase2 forward loop (local_edt_core.h:93-115)
-                    while (q >= 0) {
-                        int a = tt - ts, c = tt - u;
-                        if (a * a + th > c * c + h_u) {
-                            q--;
-                            if (q >= 0) { int bb = myB[q * RPI]; th = myH[q * RPI]; ts = bb & 0x3ff; tt = (bb >> 10) & 0x3ff; }
-                        } else break;
-                    }
-                    int w = 0;
-                    if (q >= 0) w = 1 + floor_div(u * u - ts * ts + h_u - th, 2 * (u - ts));
-                    if (w < X) {
-                        q++;
-                        ts = u; tt = w; th = h_u;
-                        myH[q * RPI] = h_u;
-                        myB[q * RPI] = u | (w << 10) | (cc[k] << 20);
-                    }
-                }
+                for (int k = 0; k < 4; k++)
+                    if (j0 + k < je) band_push<RPI>(S, b, uu[k], gg[k], cc[k] << 20, X, q, ts, tt, th);
             }
-            M(b) = xs_meta_pack(0, q + 1, 0);
+            S.M(b) = bd_meta_pack(0, q + 1, 0);
         }
         // ---- 2. pairwise merges: (0 <- 1), (2 <- 3), ... then (0..1 <- 2..3), ... until the row's envelope is described
         for (int stride = 1; stride < NB; stride <<= 1) {
             __syncthreads();
-            if ((b & (2 * stride - 1)) != 0 || b + stride >= NB) continue;
-            const int l_end = b + stride, r_end = min(b + 2 * stride, NB);
-            int kl = l_end - 1, kr = l_end;
-            int ml = 0, mr = 0;
-            while (kl >= b && (ml = M(kl), XS_HI1(ml) <= XS_LO(ml))) kl--;
-            while (kr < r_end && (mr = M(kr), XS_HI1(mr) <= XS_LO(mr))) kr++;
-            if (kl < b || kr >= r_end) continue;          // one side is empty: the other stands as it is (its first entry starts at 0)
-            int llo = XS_LO(ml), lhi = XS_HI1(ml) - 1, ltf = XS_TF(ml);
-            int rlo = XS_LO(mr), rhi = XS_HI1(mr) - 1;
-            for (;;) {
-                const int lb = entB(kl, lhi), lh = entH(kl, lhi);
-                const int rb = entB(kr, rlo), rh = entH(kr, rlo);
-                const int ls = lb & 0x3ff, lt = (lhi == llo) ? ltf : ((lb >> 10) & 0x3ff);
-                const int rs = rb & 0x3ff;
-                const int a = lt - ls, c = lt - rs;
-                if (a * a + lh > c * c + rh) {            // the left top is dominated from its own start on: pop it
-                    if (lhi > llo) { lhi--; continue; }
-                    M(kl) = xs_meta_pack(0, 0, 0);
-                    kl--;
-                    while (kl >= b && (ml = M(kl), XS_HI1(ml) <= XS_LO(ml))) kl--;
-                    if (kl < b) { M(kr) = xs_meta_pack(rlo, rhi + 1, 0); break; }   // nothing left on the left: starts at 0
-                    llo = XS_LO(ml); lhi = XS_HI1(ml) - 1; ltf = XS_TF(ml);
-                    continue;
-                }
-                const int w = 1 + floor_div(rs * rs - ls * ls + rh - lh, 2 * (rs - ls));
-                // the first entry of the right envelope ends where its successor starts
-                int rend = X;
-                if (rlo < rhi) rend = (entB(kr, rlo + 1) >> 10) & 0x3ff;
-                else {
-                    int kn = kr + 1, mn = 0;
-                    while (kn < r_end && (mn = M(kn), XS_HI1(mn) <= XS_LO(mn))) kn++;
-                    if (kn < r_end) rend = XS_TF(mn);
-                }
-                if (w >= rend) {                          // squeezed out between the left top and its own successor: drop it
-                    if (rlo < rhi) { rlo++; continue; }
-                    M(kr) = xs_meta_pack(0, 0, 0);
-                    kr++;
-                    while (kr < r_end && (mr = M(kr), XS_HI1(mr) <= XS_LO(mr))) kr++;
-                    if (kr >= r_end) { M(kl) = xs_meta_pack(llo, lhi + 1, ltf); break; }
-                    rlo = XS_LO(mr); rhi = XS_HI1(mr) - 1;
-                    continue;
-                }
-                M(kl) = xs_meta_pack(llo, lhi + 1, ltf);
-                M(kr) = xs_meta_pack(rlo, rhi + 1, w);
-                break;
-            }
+            if ((b & (2 * stride - 1)) == 0 && b + stride < NB) band_merge<RPI>(S, b, stride, NB, X);
         }
         __syncthreads();
-        // ---- 3. backward pass over this band's x range, emitted through a RPI x TW tile
+        // ---- 3. backward pass (local_edt_core.h:116-134) over this band's x range, emitted through a RPI x TW tile
         {
             const int x_lo = b * BW, x_hi = min(X, x_lo + BW) - 1;
             const bool act = x_lo <= x_hi;
-            int k = NB - 1, i = 0, lo = 0, tf = 0, es = 0, eh = 0, ecy = 0, et = 0;
-            auto load_entry = [&]() {
-                const int bb = entB(k, i);
-                eh = entH(k, i); es = bb & 0x3ff; ecy = bb >> 20;
-                et = (i == lo) ? tf : ((bb >> 10) & 0x3ff);
-            };
-            if (act) {
-                int mw = 0;
-                for (; k > 0; k--) { mw = M(k); if (XS_HI1(mw) > XS_LO(mw) && XS_TF(mw) <= x_hi) break; }
-                if (k == 0) mw = M(0);                    // the first non-empty band starts at 0: the scan cannot fall through
-                while (XS_HI1(mw) <= XS_LO(mw)) { k++; mw = M(k); }   // (band 0 itself may be empty)
-                lo = XS_LO(mw); tf = XS_TF(mw);
-                i = XS_HI1(mw) - 1;
-                while (i > lo && ((entB(k, i) >> 10) & 0x3ff) > x_hi) i--;
-                load_entry();
-            }
-            const int grp = lane / RPI * RPI;             // first lane of this band's thread group
+            EnvCursor<RPI> cur{};
+            if (act) cur.seek(S, NB, x_hi);
+            // flush geometry: thread r stores column (r % TW) of rows r / TW, r / TW + RPI / TW, ...
+            const int col = r % TW, r0 = r / TW;
+            const bool rows_full = rg * RPI + RPI <= Y;
+            const size_t row0 = ((size_t)z * Y + rg * RPI + r0) * X + col;
             for (int u = x_lo + BW - 1; u >= x_lo; u--) {
                 if (act && u <= x_hi) {
-                    const int d = u - es;
-                    tile_g[r * (TW + 1) + (u % TW)] = d * d + eh;
-                    tile_c[r * (TW + 1) + (u % TW)] = es | (ecy << 16);
-                    if (u == et && u > 0) {                // step to the previous entry of the composite envelope
-                        if (i > lo) i--;
-                        else {
-                            int mw;
-                            do { k--; mw = M(k); } while (XS_HI1(mw) <= XS_LO(mw));
-                            lo = XS_LO(mw); tf = XS_TF(mw); i = XS_HI1(mw) - 1;
-                        }
-                        load_entry();
-                    }
+                    const int d = u - cur.es;
+                    tile_g[r * (TW + 1) + (u & (TW - 1))] = d * d + cur.eh;
+                    tile_c[r * (TW + 1) + (u & (TW - 1))] = cur.es | ((cur.eb >> 20) << 16);
+                    if (u == cur.et && u > 0) cur.prev(S);
                 }
-                if ((u % TW) == 0) {
+                if ((u & (TW - 1)) == 0) {
                     __syncwarp();
-                    if (act) {
-                        const int col = r % TW, r0 = r / TW;
-                        const int xx = u + col;
-#pragma unroll 4
-                        for (int rr = r0; rr < RPI; rr += RPI / TW) {
-                            const int yy = rg * RPI + rr;
-                            if (yy < Y && xx < X) {
-                                const size_t o = ((size_t)z * Y + yy) * X + xx;
-                                g2[o] = tile_g[rr * (TW + 1) + col];
-                                cxy[o] = tile_c[rr * (TW + 1) + col];
+                    if (act && u + col < X) {
+                        int32_t *pg = g2 + row0 + u, *pc = cxy + row0 + u;
+                        const int *tg = tile_g + r0 * (TW + 1) + col, *tc = tile_c + r0 * (TW + 1) + col;
+#pragma unroll
+                        for (int k = 0; k < TW; k++) {        // RPI / (RPI / TW) = TW rows per thread
+                            if (rows_full || rg * RPI + r0 + k * (RPI / TW) < Y) {
+                                pg[(size_t)k * (RPI / TW) * X] = tg[k * (RPI / TW) * (TW + 1)];
+                                pc[(size_t)k * (RPI / TW) * X] = tc[k * (RPI / TW) * (TW + 1)];
                             }
                         }
                     }
                     __syncwarp();
                 }
             }
-            (void)grp;
+        }
+    }
+}
+
+// ---- z sweep, dense regime (EDTphase3, local_edt_core.h:137-193) ---------------------------------------------------------
+// Same banded machinery along z for volumes with obstacles in most slices, where the envelope of a z column is deep and the
+// serial scan of k_edt_zsweep (one lane = one column, 2 x Z dependent steps, stack spilling past 16 entries) runs at a small
+// fraction of the write bandwidth.  Work item = (row y, 32 consecutive x); thread = (band of real slices, x).  Loads and stores
+// are naturally coalesced along x (no tiles).  Runs only when more than a quarter of the slices hold obstacles; otherwise
+// k_edt_zsweep (below), which is bound by its writes and orders them for DRAM page locality, does the work.
+__global__ void __launch_bounds__(512)
+k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
+                    const int *__restrict__ n_slices, BandCfg cfg, int *__restrict__ work_counter)
+{
+    extern __shared__ int zs_smem[];
+    __shared__ int s_item;
+    const int X = m.X, Y = m.Y, Z = m.Z;
+    const int ns = __ldg(n_slices);
+    if (ns * 4 <= Z) return;                             // sparse regime: k_edt_zsweep
+    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW;
+    const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
+    BandStacks<32> S;
+    S.stH = zs_smem; S.stB = S.stH + NB * CAP * 32; S.meta = S.stB + NB * CAP * 32;
+    S.CAP = CAP; S.r = lane;
+    const int XG = (X + 31) / 32;
+    const int n_items = Y * XG;
+    const size_t slice = (size_t)X * Y;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        const int y = item / XG, x = (item - y * XG) * 32 + lane;
+        const bool valid = x < X;
+        const size_t base = (size_t)y * X + (valid ? x : 0);
+        // ---- forward over this band's real slices; the loads run ahead of the scan
+        {
+            const int jb = (int)((long long)ns * b / NB), je = (int)((long long)ns * (b + 1) / NB);
+            int q = -1, ts = 0, tt = 0, th = 0;
+            for (int j0 = jb; j0 < je; j0 += 4) {
+                int kk[4], hh[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    kk[k] = __ldg(&slice_list[min(j0 + k, je - 1)]);
+                    hh[k] = __ldcs(&g2[base + (size_t)kk[k] * slice]);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (j0 + k < je) band_push<32>(S, b, kk[k], hh[k], 0, Z, q, ts, tt, th);
+            }
+            S.M(b) = bd_meta_pack(0, q + 1, 0);
+        }
+        for (int stride = 1; stride < NB; stride <<= 1) {
+            __syncthreads();
+            if ((b & (2 * stride - 1)) == 0 && b + stride < NB) band_merge<32>(S, b, stride, NB, Z);
+        }
+        __syncthreads();
+        // ---- backward (local_edt_core.h:169-192) over this band's z range
+        {
+            const int z_lo = b * BW, z_hi = min(Z, z_lo + BW) - 1;
+            if (z_lo <= z_hi) {
+                EnvCursor<32> cur{};
+                cur.seek(S, NB, z_hi);
+                int c = __ldg(&cxy[base + (size_t)cur.es * slice]);
+                int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (cur.es << 22);
+                int32_t *pa = m.aux + base + (size_t)z_hi * slice, *pc = m.coc_aux + base + (size_t)z_hi * slice;
+                for (int u = z_hi; u >= z_lo; u--) {
+                    if (valid) {
+                        const int d = u - cur.es;
+                        __stcs(pa, d * d + cur.eh);
+                        __stcs(pc, coc_word);
+                    }
+                    pa -= slice; pc -= slice;
+                    if (u == cur.et && u > 0) {
+                        cur.prev(S);
+                        c = __ldg(&cxy[base + (size_t)cur.es * slice]);
+                        coc_word = (c & 0xffff) | ((c >> 16) << 11) | (cur.es << 22);
+                    }
+                }
+            }
         }
     }
 }
@@ -408,7 +525,7 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
-             int XG)
+             int XG, int banded_dense)
 {
     __shared__ int ring[WARPS_PER_CTA][2 * RING * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -419,6 +536,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     const int X = m.X, Z = m.Z, S = m.max_width;
     const size_t slice = (size_t)X * m.Y;
     const int ns = __ldg(n_slices);
+    if (ns * 4 > Z && banded_dense) return;   // dense regime: k_edt_zsweep_banded does the work
     // A CTA takes WARPS_PER_CTA adjacent 32-wide x groups of one row y at a time and its warps walk z in lockstep (one
     // __syncthreads per z step), so that every step the CTA writes ONE contiguous run per output array (1 KB / 1 KB / 2 KB at
     // 8 warps) instead of eight unrelated 128-byte lines at eight different depths: the sweep is bound by its 16 B/voxel of
@@ -531,10 +649,10 @@ int gie_edt_prepare(gie_locmap *lm)
         XsLaunch &x = lm->xs;
         x.rpi = rpi; x.threads = nwarps * 32;
         x.NB = nwarps * per_warp;
-        x.TW = rpi == 32 ? 16 : 8;
+        const int TW = rpi == 32 ? 16 : 8;               // k_edt_xsweep's tile width
         x.CAP = (m.X + x.NB - 1) / x.NB;
-        x.BW = ((m.X + x.NB - 1) / x.NB + x.TW - 1) / x.TW * x.TW;
-        x.smem = (size_t)(2 * x.NB * x.CAP * rpi + x.NB * rpi + x.NB * 2 * rpi * (x.TW + 1)) * 4;
+        x.BW = ((m.X + x.NB - 1) / x.NB + TW - 1) / TW * TW;
+        x.smem = (size_t)(2 * x.NB * x.CAP * rpi + x.NB * rpi + x.NB * 2 * rpi * (TW + 1)) * 4;
         if (rpi == 32) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
         else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
         int xs_per_sm = 1;
@@ -542,6 +660,24 @@ int gie_edt_prepare(gie_locmap *lm)
         else GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<16>, x.threads, x.smem));
         if (xs_per_sm < 1) { gie_set_error("x sweep does not fit on an SM"); return GIE_ERR_CUDA; }
         lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.Y + rpi - 1) / rpi));
+    }
+    // z sweep, dense regime: one band per warp; only when the stacks of a whole z column fit shared memory (Z <= ~880)
+    {
+        XsLaunch &zb = lm->zs;
+        const int nwarps = std::min(16, (m.Z + 31) / 32);
+        zb.rpi = 32; zb.threads = nwarps * 32; zb.NB = nwarps;
+        zb.CAP = (m.Z + zb.NB - 1) / zb.NB; zb.BW = zb.CAP;
+        zb.smem = (size_t)(2 * zb.NB * zb.CAP * 32 + zb.NB * 32) * 4;
+        int dev_max = 0;
+        GIE_CUDA_CHECK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, lm->device));
+        lm->zs_banded = zb.smem <= (size_t)dev_max && !getenv("GIE_ZS_NO_BANDED");
+        if (lm->zs_banded) {
+            GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zb.smem));
+            int per_sm = 1;
+            GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edt_zsweep_banded, zb.threads, zb.smem));
+            if (per_sm < 1) lm->zs_banded = false;
+            lm->zs_ctas = std::min(lm->num_sms * std::max(per_sm, 1), m.Y * ((m.X + 31) / 32));
+        }
     }
     lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
     GIE_CUDA_CHECK(cudaMalloc(&lm->stack_scratch, lm->stack_scratch_entries * 8));
@@ -552,7 +688,7 @@ int gie_edt_prepare(gie_locmap *lm)
 static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, int *n_slices)
 {
     const XsLaunch &x = lm->xs;
-    const XsCfg cfg{ x.NB, x.CAP, x.BW, x.TW };
+    const BandCfg cfg{ x.NB, x.CAP, x.BW };
     if (x.rpi == 32)
         k_edt_xsweep<32><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
                                                                         lm->g2, lm->cxy, cfg, lm->work_counters + 0);
@@ -561,13 +697,30 @@ static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, 
                                                                         lm->g2, lm->cxy, cfg, lm->work_counters + 0);
 }
 
+// dense regime first (returns at once when few slices hold obstacles), then the write-ordered serial sweep (returns at once in
+// the dense regime when the banded kernel is available)
+static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int *n_slices)
+{
+    const int XG = (m.X + 31) / 32;
+    const int L = m.X > m.Z ? m.X : m.Z;
+    if (lm->zs_banded) {
+        const BandCfg cfg{ lm->zs.NB, lm->zs.CAP, lm->zs.BW };
+        k_edt_zsweep_banded<<<lm->zs_ctas, lm->zs.threads, lm->zs.smem, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, cfg,
+                                                                                     lm->work_counters + 2);
+        lm->launches++;
+    }
+    k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
+                                                                      lm->work_counters + 1, m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG,
+                                                                      lm->zs_banded ? 1 : 0);
+    lm->launches++;
+}
+
 // The two halves of the batch EDT as separate launches, for the multi-GPU path (gie-mapping_b200/sharded.py): the y and x
 // sweeps are local to a z-slab of the volume, the z sweep needs whole z columns and runs after the slabs were re-partitioned.
 int gie_launch_edt_xy(gie_locmap *lm)
 {
     const LocDev &m = lm->d;
     const int WY = (m.Y + 31) / 32;
-    const int L = m.X > m.Z ? m.X : m.Z;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     launch_ybits(lm, WY);
@@ -582,14 +735,11 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
 {
     LocDev m = lm->d;
     if (max_width_override > 0) m.max_width = max_width_override;
-    const int XG = (m.X + 31) / 32;
-    const int L = m.X > m.Z ? m.X : m.Z;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
-    k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
-                                                                      lm->work_counters + 1, m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG);
-    lm->launches += 2;
+    launch_zsweep(lm, m, slice_list, n_slices);
+    lm->launches += 1;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
@@ -597,8 +747,7 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
 int gie_launch_batch_edt(gie_locmap *lm)
 {
     const LocDev &m = lm->d;
-    const int WY = (m.Y + 31) / 32, XG = (m.X + 31) / 32;
-    const int L = m.X > m.Z ? m.X : m.Z;
+    const int WY = (m.Y + 31) / 32;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     {
@@ -613,11 +762,9 @@ int gie_launch_batch_edt(gie_locmap *lm)
     }
     {
         StageTimer t(lm, GIE_ST_EDT_Z);
-        k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices,
-                                                                          (uint2 *)lm->stack_scratch, L, lm->work_counters + 1,
-                                                                          m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG);
+        launch_zsweep(lm, m, slice_list, n_slices);
     }
-    lm->launches += 5;
+    lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }

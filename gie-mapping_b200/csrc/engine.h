@@ -4,7 +4,7 @@
 #include "../../include/gie_b200.h"
 #include <string>
 
-struct XsLaunch { int rpi = 32, threads = 0, NB = 0, CAP = 0, BW = 0, TW = 0; size_t smem = 0; };   // x-sweep launch shape (edt.cu)
+struct XsLaunch { int rpi = 32, threads = 0, NB = 0, CAP = 0, BW = 0; size_t smem = 0; };   // launch shape of a banded sweep (edt.cu)
 
 struct gie_locmap {
     LocDev d{};                 // device view, passed by value to kernels (as the reference passes LocMap)
@@ -23,6 +23,9 @@ struct gie_locmap {
     int edt_ctas = 0;                     // persistent grid of the z sweep
     int xs_ctas = 0;                      // persistent grid of the x sweep
     XsLaunch xs;
+    XsLaunch zs;                          // banded z sweep (dense regime)
+    bool zs_banded = false;
+    int zs_ctas = 0;
     int *work_counters = nullptr;         // device: [4]
     // staging for *_host entry points
     float *stage_dev = nullptr;

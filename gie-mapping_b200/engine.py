@@ -175,6 +175,13 @@ class LocMap:
     def edt_z_sweep(self, max_width_override=0):
         _check(self.lib.gie_edt_z_sweep(self._h, int(max_width_override)))
 
+    def edt_slice_columns(self):
+        """int32 [Z]: obstacle-bearing columns per z-slice found by the last batch EDT (0 = the sweeps skipped the slice)."""
+        ptr, nbytes = self.device_ptr(ARR_EDT_NCOLS)
+        out = np.empty(self._local_size[2], np.int32)
+        _check(self.lib.gie_locmap_download(self._h, ARR_EDT_NCOLS, _hostptr(out)))
+        return out
+
     def profile_enable(self, on=True):
         _check(self.lib.gie_profile_enable(self._h, int(on)))
 

@@ -48,10 +48,16 @@ def lib():
         l.gor_take_changed.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         l.gor_num_blocks.argtypes = [C.c_void_p]
         l.gor_export_blocks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        l.gor_set_threads.argtypes = [C.c_int]
         l.gor_cuda_atan2f.restype = C.c_float
         l.gor_cuda_atan2f.argtypes = [C.c_float, C.c_float]
         _LIB = l
     return _LIB
+
+
+def set_threads(n):
+    """Host threads for the oracle's batch EDT (OpenMP over columns); everything else is serial."""
+    lib().gor_set_threads(int(n))
 
 
 def _p(a):
