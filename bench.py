@@ -5,14 +5,15 @@
 
 A "step" is one frame of VOLMAPNODE::publishMap's hot path (reference src/volumetric_mapper.cpp:138-224) on a moving
 synthetic sensor (gie-mapping_b200/scenes.py).  N=1 runs the headline configuration cfg4 (512^3 @ 0.1 m, 65 536-point
-OS-32 scan, full wavefronts).  N>1 runs N independent replicas, one per GPU (weak scaling; the sharded 1024^3
-configuration is not built yet — DESIGN.md §8).
+OS-32 scan, full wavefronts).  N>1 runs ONE volume of the multi-GPU configuration (cfg5: 1024 x 1024 x 1016 @ 0.1 m,
+131 072-ray scan) sharded over the N GPUs (gie-mapping_b200/sharded.py): strong scaling; rank 0 also times the
+same frames on its GPU alone, so the line carries its own single-GPU figure.
 
   value      frames/s with the sensor frames already resident in HBM (CUDA events on the launch stream)
   e2e        frames/s through the host-buffer C ABI: pinned host points -> H2D inside the timed region, and a D2H read of
              the frame's result record (device status + wavefront statistics)
-  roofline   algorithmic bytes of the dominant kernel / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the C oracle (oracle/gie_oracle.c, a port) on a bounded sample, one host core
+  roofline   bytes the batch-DT sweeps have to move for the frames at hand / their CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the C oracle (oracle/gie_oracle.c, a port) at the full volume: one thread, and all host cores for the batch EDT
 
 --impl reference times the reference's own CUDA sources recompiled for sm_100a (oracle/_ref/ref_driver_fast: original
 Release flags, cuTT replaced by a gather shim) on the same frames; the reference has no CPU implementation of this path.
@@ -219,41 +220,146 @@ def cpp_host_leg(gie, cfg, frames, warmup):
         return {"error": repr(e)[:300]}
 
 
-def sharded_edt_leg(world, rank):
-    """BASELINE configs[4] shape (1024^3-class volume sharded over the GPUs of the box): the batch EDT with its z-slab <->
-    y-slab NCCL all-to-all (gie-mapping_b200/sharded.py).  Extra information, not part of `value`: the per-frame pipeline
-    is not sharded yet, N GPUs run N replicas of it."""
+def run_sharded(args, gie, world, rank, local_rank):
+    """N > 1: ONE local volume of BASELINE configs[4] (1024 x 1024 x 1016 @ 0.1 m, 64 x 2048-ray scan) sharded over the N GPUs
+    (gie-mapping_b200/sharded.py): strong scaling.  Rank 0 also times the same frames on its own GPU alone afterwards, so the
+    line carries its own single-GPU figure for the same workload."""
     import torch
     import torch.distributed as dist
     from gie_mapping_b200 import sharded
-    X, Y, Z = 1024, 1024, 1016          # Z <= 1022 (coc codec) and divisible by 2, 4, 8
-    try:
-        eng = sharded.ShardedBatchEDT(0.1, (X, Y, Z), cutoff_grids_sq=2500)
-        g = torch.Generator(device="cuda")
-        g.manual_seed(1234 + rank)
-        eng.set_slab_types(torch.where(torch.rand((Z // world, Y, X), device="cuda", generator=g) < 0.001, 2, 1).to(torch.int8))
-        for _ in range(2):
-            eng.update()
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    cfg = gie.scenes.make_config(args.config if args.config != "cfg4" else "cfg5")
+    X, Y, Z = cfg["local_size"]
+    nvox = X * Y * Z
+    nframes = args.warmup + args.steps
+    frames = gie.scenes.make_frames(cfg, nframes, seed=42) if rank == 0 else [None] * nframes
+    host_in = [torch.from_numpy(np.ascontiguousarray(f["points"], np.float32)).pin_memory() for f in frames] if rank == 0 else []
+    dev_in = [h.to(dev) for h in host_in]
+
+    def barrier():
+        dist.barrier()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        reps, b0 = 4, eng.exchanged_bytes
+
+    def timed(make, device_resident):
+        mp = make()
+        for k in range(args.warmup):
+            mp.publishMap(frames[k], device_input=dev_in[k].data_ptr() if (rank == 0 and device_resident) else None)
+        if rank == 0:
+            mp.hash_map.sync()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            eng.update()
-        e1.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out = {"volume": [X, Y, Z], "occupancy": 0.001, "n_gpus": world, "ms_per_update": float(t.item()),
-               "mvoxels_per_s": X * Y * Z / float(t.item()) / 1e3, "bytes_out_per_rank_per_update": (eng.exchanged_bytes - b0) // reps,
-               "collective": "2 + 2 all_to_all_single (NCCL) per update" if world > 1 else "none"}
-        eng.close()
-        return out
-    except Exception as e:     # never lose the headline line to the extra leg
-        return {"error": repr(e)[:300]}
+        sampler.active = True
+        e0.record(stream)
+        for k in range(args.warmup, nframes):
+            if rank == 0 and not device_resident:
+                f = dict(frames[k])
+                f["points"] = host_in[k].numpy()
+                mp.publishMap(f)
+                mp.hash_map.sync()
+                mp.hash_map.wave_stats()
+            else:
+                mp.publishMap(frames[k], device_input=dev_in[k].data_ptr() if rank == 0 else None)
+        e1.record(stream)
+        barrier()
+        sampler.active = False
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), mp
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    make_sharded = lambda: sharded.ShardedMapper(cfg, rank=rank, world=world)
+    ms_dev, mp = timed(make_sharded, True)
+    launches = mp.owner.loc_map.launch_count() if rank == 0 else 0
+    wave_stats = mp.hash_map.wave_stats() if rank == 0 else None
+    nblocks = mp.hash_map.num_blocks() if rank == 0 else None
+    bytes_rx = mp.bytes_received
+    mp.close()
+    ms_e2e, mp = timed(make_sharded, False)
+    # stage profile of the sharded frame: the owner's stages on rank 0, the slab sweeps on every rank (max over ranks)
+    if rank == 0:
+        mp.owner.loc_map.profile_enable(True)
+    _check_slab = mp.slab
+    gie.load_library().gie_profile_enable(_check_slab._h, 1)
+    prof, sweeps = {}, 0.0
+    import ctypes as C
+    reps = min(10, args.steps)
+    for k in range(nframes - reps, nframes):
+        mp.publishMap(frames[k], device_input=dev_in[k].data_ptr() if rank == 0 else None)
+        ms = np.zeros(len(gie.STAGE_NAMES), np.float32)
+        gie.load_library().gie_profile_last(_check_slab._h, ms.ctypes.data_as(C.c_void_p))
+        sweeps += float(ms[gie.STAGE_NAMES.index("edt_x")] + ms[gie.STAGE_NAMES.index("edt_z")]) / reps
+        if rank == 0:
+            for name, v in mp.owner.loc_map.profile_last().items():
+                prof[name] = prof.get(name, 0.0) + v / reps
+    t = torch.tensor([sweeps], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sweeps_max = float(t.item())
+    rx = torch.tensor([float(bytes_rx)], device=dev)
+    dist.all_reduce(rx, op=dist.ReduceOp.MAX)
+    mp.close()
+    sampler.stop()
+    barrier()
+    # the same frames on rank 0's GPU alone (the other ranks wait)
+    single = None
+    if rank == 0 and not args.no_single_gpu_leg:
+        try:
+            m1 = gie.Mapper(cfg)
+            m1.loc_map.set_stream(stream.cuda_stream)
+            for k in range(args.warmup):
+                m1.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+            m1.hash_map.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(args.warmup, nframes):
+                m1.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+            e1.record(stream)
+            torch.cuda.synchronize()
+            single = {"ms_per_step": e0.elapsed_time(e1) / args.steps}
+            single["value"] = 1000.0 / single["ms_per_step"]
+            m1.loc_map.profile_enable(True)
+            sp = {}
+            for k in range(nframes - reps, nframes):
+                m1.publishMap(frames[k], device_input=dev_in[k].data_ptr())
+                for name, v in m1.loc_map.profile_last().items():
+                    sp[name] = sp.get(name, 0.0) + v / reps
+            single["stage_ms"] = sp
+            m1.close()
+        except Exception as e:
+            single = {"error": repr(e)[:300]}
+    barrier()
+    if rank == 0:
+        fps, fps_e2e = 1000.0 / ms_dev, 1000.0 / ms_e2e
+        peak, peak_src = measured_peak()
+        line = {"metric": "EDT+OGM frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f32", "data": "synthetic",
+                "config": {"workload": workload_string(cfg, frames),
+                           "parallelism": f"ONE local volume sharded over {world} GPUs: {world} slabs of {Y // world} rows y; dense half (x and z sweeps of the "
+                                          "batch EDT) on every rank, y pass broadcast from rank 0 (NCCL, obstacle-bearing slices only), sparse half "
+                                          "(ray cast, hash merge, wavefronts) on rank 0 reading the slabs through CUDA IPC over NVLink",
+                           "l2": "per-frame working set (>= 8.5 GB of batch-EDT output) exceeds the 126 MB L2; no explicit flush"},
+                "mvoxels_per_s": fps * nvox / 1e6,
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": int(np.mean([h.numel() * 4 for h in host_in])) + 28, "d2h_bytes_per_step": 4 + 64},
+                "gpu_launches": int(launches), "stage_ms_rank0": prof, "slab_sweeps_ms_max_over_ranks": sweeps_max,
+                "broadcast_bytes_per_frame": float(rx.item()) / max(1, nframes), "wave_stats": wave_stats, "blocks": nblocks,
+                "single_gpu_same_workload": single,
+                "strong_scaling": ({"speedup": single["ms_per_step"] / ms_dev, "efficiency": single["ms_per_step"] / ms_dev / world}
+                                   if single and "ms_per_step" in single else None),
+                "roofline": {"bound": "hbm", "kernel": "slab sweeps = k_edt_xsweep + k_edt_zsweep on the slab of the slowest rank",
+                             "achieved": (batch_dt_bytes_per_voxel(0.0) - 1.75) * nvox / world / (sweeps_max * 1e-3) / 1e9 if sweeps_max > 0 else 0.0,
+                             "peak": peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
+                             "frac": ((batch_dt_bytes_per_voxel(0.0) - 1.75) * nvox / world / (sweeps_max * 1e-3) / 1e9 / peak) if sweeps_max > 0 else 0.0,
+                             "traffic": None,
+                             "note": "lower bound of the bytes of one slab: 8 B/voxel of aux + coc_aux written (the slice-dependent x-sweep output and "
+                                     "z-sweep input are left out); per-GPU figure"},
+                "clocks": sampler.summary()}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def run_reference(args, gie, cfg, frames):
@@ -309,17 +415,24 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense-case", action="store_true")
-    ap.add_argument("--no-sharded-edt", action="store_true", help="skip the sharded batch-EDT leg that runs when N > 1")
-    ap.add_argument("--sharded-edt", action="store_true", help="run that leg at N = 1 too (82 GB of device memory)")
+    ap.add_argument("--no-single-gpu-leg", action="store_true", help="N > 1: skip timing the same frames on rank 0's GPU alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
     gie = load_pkg()
-    cfg = gie.scenes.make_config(args.config)
-    nframes = args.warmup + args.steps
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        if args.impl == "reference":
+            if rank == 0:   # the reference cannot hold a 1024-class volume (10-bit z of its coc codec, dist_sq sentinel)
+                print(json.dumps({"impl": "reference", "unavailable": "the reference is single-GPU and cannot run the sharded 1024 x 1024 x 1016 "
+                                  "volume of the multi-GPU configuration (coc codec 11/11/10 bit, local_batch.h:12-17,51-58)"}), flush=True)
+            return
+        run_sharded(args, gie, world, rank, local_rank)
+        return
+    cfg = gie.scenes.make_config(args.config)
+    nframes = args.warmup + args.steps
 
     frames = gie.scenes.make_frames(cfg, nframes, seed=42 + rank)
     if args.impl == "reference":
@@ -462,8 +575,6 @@ def main():
             "stage_ms": prof, "outside_kernels_ms": ms_dev - stage_sum,
             "wave_stats": wave_stats, "blocks": nblocks,
             "roofline": roofline, "clocks": clocks}
-    if not args.no_sharded_edt and (world > 1 or args.sharded_edt):
-        line["sharded_batch_edt"] = sharded_edt_leg(world, rank)
     if rank == 0 and world == 1:
         line["e2e_cpp_host"] = cpp_host_leg(gie, cfg, frames, args.warmup)
     if rank == 0:

@@ -70,16 +70,19 @@ ArrInfo arr_info(gie_locmap *lm, int which)
 {
     const LocDev &m = lm->d;
     size_t n = (size_t)m.N;
+    const size_t ns = (size_t)m.Z * m.ysn * m.X;   // batch-EDT arrays: the rows this map holds (== n for a whole map)
+    if (lm->slab_only && which != GIE_ARR_AUX && which != GIE_ARR_COC_AUX && which != GIE_ARR_EDT_G2 && which != GIE_ARR_EDT_CXY &&
+        which != GIE_ARR_EDT_NCOLS) return { nullptr, 0 };
     switch (which) {
         case GIE_ARR_RAY_COUNT: return { m.ray_count, n * 4 };
         case GIE_ARR_INST_TYPE: return { m.inst_type, n };
         case GIE_ARR_GLB_TYPE: return { m.glb_type, n };
         case GIE_ARR_EDT: return { m.edt, n * 4 };
-        case GIE_ARR_AUX: return { m.aux, n * 4 };
-        case GIE_ARR_COC_AUX: return { m.coc_aux, n * 4 };
+        case GIE_ARR_AUX: return { m.aux, ns * 4 };
+        case GIE_ARR_COC_AUX: return { m.coc_aux, ns * 4 };
         case GIE_ARR_PAIR: return { m.pair, n * 8 };
-        case GIE_ARR_EDT_G2: return { lm->g2, n * 4 };
-        case GIE_ARR_EDT_CXY: return { lm->cxy, n * 4 };
+        case GIE_ARR_EDT_G2: return { lm->g2, ns * 4 };
+        case GIE_ARR_EDT_CXY: return { lm->cxy, ns * 4 };
         case GIE_ARR_EDT_NCOLS: return { lm->edt_meta, (size_t)m.Z * 4 };
         default: return { nullptr, 0 };
     }
@@ -112,6 +115,7 @@ int gie_locmap_create(gie_locmap **out, float voxel_size, int X, int Y, int Z, u
     m.max_width = X + Y + Z;
     m.max_loc_dist_sq = X * X + Y * Y + Z * Z;
     m.half = make_int3(X / 2, Y / 2, Z / 2);
+    m.ys0 = 0; m.ysn = Y; m.n_slabs = 1; m.slab_rows = Y;
     GIE_CUDA_CHECK(cudaGetDevice(&lm->device));
     GIE_CUDA_CHECK(cudaDeviceGetAttribute(&lm->num_sms, cudaDevAttrMultiProcessorCount, lm->device));
     size_t n = (size_t)m.N;
@@ -145,8 +149,10 @@ int gie_locmap_destroy(gie_locmap *lm)
     LocDev &m = lm->d;
     cudaFree(m.ray_count); cudaFree(m.inst_type); cudaFree(m.glb_type); cudaFree(m.edt); cudaFree(m.aux);
     cudaFree(m.coc_aux); cudaFree(m.wave_layer); cudaFree(m.pair);
-    cudaFree(lm->ytab); cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->col_list); cudaFree(lm->edt_meta); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
-    cudaFree(lm->stage_dev);
+    if (!lm->edt_inputs_aliased) { cudaFree(lm->ytab); cudaFree(lm->col_list); cudaFree(lm->edt_meta); }
+    cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
+    for (int i = 0; i < lm->n_ipc_opened; i++) cudaIpcCloseMemHandle(lm->ipc_opened[i]);
+    cudaFree(lm->stage_dev); cudaFree(lm->ray_scratch);
     for (int i = 0; i < GIE_ST_COUNT; i++) for (int j = 0; j < 2; j++) if (lm->ev[i][j]) cudaEventDestroy(lm->ev[i][j]);
     delete lm;
     return GIE_OK;
@@ -236,6 +242,18 @@ int gie_locmap_device_ptr(gie_locmap *lm, int which, void **dev_ptr, size_t *byt
 int gie_locmap_download(gie_locmap *lm, int which, void *host_out)
 {
     if (!lm || !host_out) return GIE_ERR_INVALID_ARG;
+    const LocDev &m = lm->d;
+    if (m.n_slabs > 1 && (which == GIE_ARR_AUX || which == GIE_ARR_COC_AUX)) {
+        // assembled from the slabs (own or peer): slab g is [Z][slab_rows][X], the volume is [Z][Y][X]
+        const size_t row = (size_t)m.X * 4, slab_pitch = row * m.slab_rows, vol_pitch = row * m.Y;
+        for (int g = 0; g < m.n_slabs; g++) {
+            const int32_t *src = which == GIE_ARR_AUX ? m.aux_s[g] : m.coc_s[g];
+            GIE_CUDA_CHECK(cudaMemcpy2DAsync((char *)host_out + (size_t)g * slab_pitch, vol_pitch, src, slab_pitch, slab_pitch, m.Z,
+                                             cudaMemcpyDeviceToHost, lm->stream));
+        }
+        GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream));
+        return GIE_OK;
+    }
     ArrInfo a = arr_info(lm, which);
     if (!a.p) { gie_set_error("unknown array id"); return GIE_ERR_INVALID_ARG; }
     GIE_CUDA_CHECK(cudaMemcpyAsync(host_out, a.p, a.bytes, cudaMemcpyDeviceToHost, lm->stream));
@@ -248,6 +266,7 @@ int gie_locmap_upload_glb_type(gie_locmap *lm, const signed char *src)
     if (!lm || !src) return GIE_ERR_INVALID_ARG;
     GIE_CUDA_CHECK(cudaMemcpyAsync(lm->d.glb_type, src, (size_t)lm->d.N, cudaMemcpyHostToDevice, lm->stream));
     GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream));
+    lm->glb_type_foreign = true;
     return GIE_OK;
 }
 
@@ -319,6 +338,10 @@ int gie_hashmap_create(gie_hashmap **out, gie_locmap *lm, int bucket_max, int bl
     GIE_CUDA_CHECK(cudaMemsetAsync(h.touched, 0, hm->tab_entries, s));
     GIE_CUDA_CHECK(cudaMalloc(&hm->merge_list, hm->tab_entries * sizeof(int)));
     GIE_CUDA_CHECK(cudaMalloc(&hm->merge_count, sizeof(int)));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->prev_list, hm->tab_entries * sizeof(int)));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->prev_count, sizeof(int)));
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->merge_count, 0, sizeof(int), s));
+    GIE_CUDA_CHECK(cudaMemsetAsync(hm->prev_count, 0, sizeof(int), s));
     GIE_CUDA_CHECK(cudaMalloc(&h.dirty, (size_t)block_max));
     GIE_CUDA_CHECK(cudaMemsetAsync(h.dirty, 0, (size_t)block_max, s));
     GIE_CUDA_CHECK(cudaMalloc(&hm->changed_list, (size_t)block_max * sizeof(int)));
@@ -342,13 +365,123 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     HashDev &h = hm->d;
     cudaFree(h.keys); cudaFree(h.vals); cudaFree(h.block_count); cudaFree(h.status); cudaFree(h.block_keys);
     cudaFree(h.occ_val); cudaFree(h.vox_type); cudaFree(h.update_ct); cudaFree(h.coc_glb); cudaFree(h.dist_sq);
-    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched); cudaFree(hm->merge_list); cudaFree(hm->merge_count); cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
+    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched); cudaFree(hm->merge_list); cudaFree(hm->merge_count); cudaFree(hm->prev_list); cudaFree(hm->prev_count); cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
     cudaFree(hm->cseed_key); cudaFree(hm->counters); cudaFree(hm->barrier); cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
     cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list); cudaFree(hm->blk_count);
     cudaFreeHost(hm->status_host); cudaFreeHost(hm->stats_host);
     if (hm->lm->hm == hm) hm->lm->hm = nullptr;
     delete hm;
+    return GIE_OK;
+}
+
+// ---- volumes sharded over GPUs (no reference counterpart: the reference is single-GPU) ----------------------------------
+int gie_locmap_create_slab(gie_locmap **out, int X, int Y, int Z, int row0, int rows)
+{
+    if (!out || X < 1 || Y < 1 || Z < 1 || row0 < 0 || rows < 1 || row0 + rows > Y || (row0 % 32) != 0) {
+        gie_set_error("bad slab arguments (rows must start at a multiple of 32 inside the volume)");
+        return GIE_ERR_INVALID_ARG;
+    }
+    if (X > 1024 || Y > 1024 || Z > 1022) { gie_set_error("local map size too big (max 1024 x 1024 x 1022)"); return GIE_ERR_SIZE_UNSUPPORTED; }
+    gie_locmap *lm = new gie_locmap();
+    LocDev &m = lm->d;
+    m.X = X; m.Y = Y; m.Z = Z; m.N = X * Y * Z; m.w = 1.f;
+    m.max_width = X + Y + Z;
+    m.max_loc_dist_sq = X * X + Y * Y + Z * Z;
+    m.ys0 = row0; m.ysn = rows; m.n_slabs = 1; m.slab_rows = Y;
+    lm->slab_only = true;
+    GIE_CUDA_CHECK(cudaGetDevice(&lm->device));
+    GIE_CUDA_CHECK(cudaDeviceGetAttribute(&lm->num_sms, cudaDevAttrMultiProcessorCount, lm->device));
+    const size_t n = (size_t)Z * rows * X;
+    GIE_CUDA_CHECK(cudaMalloc(&m.aux, n * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&m.coc_aux, n * 4));
+    GIE_CUDA_CHECK(cudaMemset(m.aux, 0, n * 4));
+    GIE_CUDA_CHECK(cudaMemset(m.coc_aux, 0, n * 4));
+    int rc = gie_edt_prepare(lm);
+    if (rc != GIE_OK) return rc;
+    *out = lm;
+    return GIE_OK;
+}
+
+int gie_slab_alias_inputs(gie_locmap *slab, gie_locmap *owner)
+{
+    if (!slab || !owner || !slab->slab_only || slab->device != owner->device || slab->d.X != owner->d.X || slab->d.Y != owner->d.Y ||
+        slab->d.Z != owner->d.Z) { gie_set_error("slab and owner maps do not match"); return GIE_ERR_INVALID_ARG; }
+    if (!slab->edt_inputs_aliased) { cudaFree(slab->ytab); cudaFree(slab->col_list); cudaFree(slab->edt_meta); }
+    slab->ytab = owner->ytab; slab->col_list = owner->col_list; slab->edt_meta = owner->edt_meta;
+    slab->edt_inputs_aliased = true; slab->edt_compact = false;
+    slab->stream = owner->stream;
+    return GIE_OK;
+}
+
+int gie_slab_input_buffers(gie_locmap *slab, void **ytab_dev, size_t *ytab_bytes, void **col_list_dev, size_t *col_bytes, void **meta_dev,
+                           size_t *meta_bytes)
+{
+    if (!slab) return GIE_ERR_INVALID_ARG;
+    const LocDev &m = slab->d;
+    if (ytab_dev) *ytab_dev = slab->ytab;
+    if (ytab_bytes) *ytab_bytes = (size_t)m.Z * ((m.Y + 31) / 32) * m.X * 8;
+    if (col_list_dev) *col_list_dev = slab->col_list;
+    if (col_bytes) *col_bytes = (size_t)m.Z * m.X * 4;
+    if (meta_dev) *meta_dev = slab->edt_meta;
+    if (meta_bytes) *meta_bytes = (size_t)(2 * m.Z + 8) * 4;
+    return GIE_OK;
+}
+
+int gie_slab_set_compact(gie_locmap *slab, int compact)
+{
+    if (!slab || !slab->slab_only) return GIE_ERR_INVALID_ARG;
+    slab->edt_compact = compact != 0;
+    return GIE_OK;
+}
+
+int gie_edt_pack(gie_locmap *lm, void *ytab_compact_dev, void *col_compact_dev)
+{
+    if (!lm || lm->slab_only) return GIE_ERR_INVALID_ARG;
+    return gie_launch_edt_pack(lm, (unsigned long long *)ytab_compact_dev, (int *)col_compact_dev);
+}
+
+int gie_edt_slab_sweeps(gie_locmap *slab, int max_width)
+{
+    if (!slab || max_width < 0) return GIE_ERR_INVALID_ARG;
+    return gie_launch_edt_slab(slab, max_width);
+}
+
+int gie_ipc_export(void *dev_ptr, unsigned char handle64[64])
+{
+    if (!dev_ptr || !handle64) return GIE_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    GIE_CUDA_CHECK(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return GIE_OK;
+}
+
+int gie_locmap_attach_slabs(gie_locmap *lm, int n_slabs, int slab_rows, void *const *aux_dev, void *const *coc_dev,
+                            const unsigned char *aux_handles, const unsigned char *coc_handles)
+{
+    if (!lm || lm->slab_only || n_slabs < 2 || n_slabs > 8 || slab_rows < 32 || slab_rows % 32 || slab_rows * n_slabs != lm->d.Y) {
+        gie_set_error("bad slab layout (2..8 slabs of equal height, a multiple of 32 rows)");
+        return GIE_ERR_INVALID_ARG;
+    }
+    LocDev &m = lm->d;
+    for (int g = 0; g < n_slabs; g++) {
+        void *pa = aux_dev ? aux_dev[g] : nullptr, *pc = coc_dev ? coc_dev[g] : nullptr;
+        if (!pa) {   // a peer process' slab: map it
+            if (!aux_handles || !coc_handles) { gie_set_error("slab without pointer or IPC handle"); return GIE_ERR_INVALID_ARG; }
+            cudaIpcMemHandle_t ha, hc;
+            memcpy(&ha, aux_handles + 64 * g, 64); memcpy(&hc, coc_handles + 64 * g, 64);
+            GIE_CUDA_CHECK(cudaIpcOpenMemHandle(&pa, ha, cudaIpcMemLazyEnablePeerAccess));
+            GIE_CUDA_CHECK(cudaIpcOpenMemHandle(&pc, hc, cudaIpcMemLazyEnablePeerAccess));
+            lm->ipc_opened[lm->n_ipc_opened++] = pa; lm->ipc_opened[lm->n_ipc_opened++] = pc;
+        }
+        m.aux_s[g] = (int32_t *)pa; m.coc_s[g] = (int32_t *)pc;
+    }
+    // the whole-volume copies of the batch-EDT arrays are not needed any more
+    GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream));
+    cudaFree(m.aux); cudaFree(m.coc_aux); cudaFree(lm->g2); cudaFree(lm->cxy);
+    m.aux = nullptr; m.coc_aux = nullptr; lm->g2 = nullptr; lm->cxy = nullptr;
+    m.n_slabs = n_slabs; m.slab_rows = slab_rows;
     return GIE_OK;
 }
 
@@ -511,6 +644,7 @@ int gie_hashmap_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int st
 int gie_edt_batch_update(gie_locmap *lm)
 {
     if (!lm) return GIE_ERR_INVALID_ARG;
+    if (lm->d.n_slabs > 1 || lm->slab_only) { gie_set_error("sharded volume: use gie_edt_pack + gie_edt_slab_sweeps"); return GIE_ERR_INVALID_ARG; }
     return gie_launch_batch_edt(lm);
 }
 int gie_edt_xy_sweeps(gie_locmap *lm)

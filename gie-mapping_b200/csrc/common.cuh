@@ -46,6 +46,14 @@ struct LocDev {
     int32_t *coc_aux;   // batch coc, local coords packed 11/11/10     == reference _coc_idx_aux
     int32_t *wave_layer;
     unsigned long long *pair;  // (dist_sq << 32) | wave-range coc id  == reference _dist_id_pair
+    // --- volumes sharded over GPUs ---
+    // A slab map holds rows [ys0, ys0 + ysn) of the batch-EDT arrays (g2, cxy, aux, coc_aux are [Z][ysn][X]); the sweeps
+    // take their work items from that range.  A whole map has ys0 = 0, ysn = Y.
+    int ys0, ysn;
+    // The map that runs the sparse stages of a sharded volume reads the batch-EDT result (aux, coc_aux) out of the slabs,
+    // its own or a peer GPU's (mapped through CUDA IPC): n_slabs > 1, slab g holds rows [g * slab_rows, (g + 1) * slab_rows).
+    int n_slabs, slab_rows;
+    int32_t *aux_s[8], *coc_s[8];
 };
 
 struct HashDev {
@@ -135,6 +143,19 @@ __host__ __device__ __forceinline__ bool gie_inside_loc(const LocDev &m, int3 c)
     return !(c.x < 0 || c.x >= m.X || c.y < 0 || c.y >= m.Y || c.z < 0 || c.z >= m.Z);
 }
 __host__ __device__ __forceinline__ int gie_lidx(const LocDev &m, int3 c) { return c.x + c.y * m.X + c.z * m.X * m.Y; }
+// batch-EDT result of local voxel c: the map's own array, or the slab (possibly on a peer GPU) that holds row c.y
+__host__ __device__ __forceinline__ int32_t *gie_aux_ptr(const LocDev &m, int3 c)
+{
+    if (m.n_slabs <= 1) return m.aux + gie_lidx(m, c);
+    const int g = c.y / m.slab_rows;
+    return m.aux_s[g] + ((size_t)c.z * m.slab_rows + (c.y - g * m.slab_rows)) * m.X + c.x;
+}
+__host__ __device__ __forceinline__ int32_t *gie_coc_aux_ptr(const LocDev &m, int3 c)
+{
+    if (m.n_slabs <= 1) return m.coc_aux + gie_lidx(m, c);
+    const int g = c.y / m.slab_rows;
+    return m.coc_s[g] + ((size_t)c.z * m.slab_rows + (c.y - g * m.slab_rows)) * m.X + c.x;
+}
 // voxmap_utils.cuh:161-172
 __host__ __device__ __forceinline__ bool gie_invalid_dist_glb(int d) { return d < 0 || d >= 900000; }
 __host__ __device__ __forceinline__ bool gie_invalid_coc_glb(int3 c) { return c.x > 900000 || c.y > 900000 || c.z > 900000; }

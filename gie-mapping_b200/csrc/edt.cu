@@ -27,7 +27,6 @@
 
 namespace {
 
-constexpr int WARPS_PER_CTA = 8;
 constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
 constexpr int RING = 16;      // stack entries per lane kept in shared memory
 
@@ -339,7 +338,7 @@ template <int RPI>
 __global__ void __launch_bounds__(512)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
-             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter)
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter, int compact)
 {
     constexpr int TW = RPI == 32 ? 16 : 8;               // tile width: a row segment of 64 / 32 bytes per store
     extern __shared__ int xs_smem[];
@@ -353,8 +352,9 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
     S.meta = S.stB + NB * CAP * RPI;                     // [NB][RPI]
     S.CAP = CAP; S.r = r;
     int *tile_g = S.meta + NB * RPI + b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);   // [NB][2][RPI][TW + 1]
-    const int X = m.X, Y = m.Y;
-    const int RG = (Y + RPI - 1) / RPI;                  // row groups per slice
+    const int X = m.X;
+    const int YS0 = m.ys0, YSN = m.ysn;                  // rows of this map (a slab of a sharded volume, or all of them)
+    const int RG = (YSN + RPI - 1) / RPI;                // row groups per slice
     const int n_items = __ldg(n_slices) * RG;
     for (;;) {
         __syncthreads();   // the previous item's stacks and tiles are no longer read
@@ -364,10 +364,11 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
         if (item >= n_items) break;
         const int zi = item / RG, rg = item - zi * RG;
         const int z = __ldg(&slice_list[zi]);
-        const int y = rg * RPI + r;
+        const int y = YS0 + rg * RPI + r;
         const int wy = y >> 5, p = y & 31;               // ytab word and bit of this row
-        const unsigned long long *trow = ytab + ((size_t)z * WY + wy) * X;
-        const int *cols = col_list + (size_t)z * X;
+        const int zp = compact ? zi : z;                 // plane of ytab / col_list: compacted to the real slices when received from a peer
+        const unsigned long long *trow = ytab + ((size_t)zp * WY + wy) * X;
+        const int *cols = col_list + (size_t)zp * X;
         const int nc = __ldg(&n_cols[z]);
         // ---- 1. forward pass over this band's real columns
         {
@@ -412,8 +413,8 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
             if (act) cur.seek(S, NB, x_hi);
             // flush geometry: thread r stores column (r % TW) of rows r / TW, r / TW + RPI / TW, ...
             const int col = r % TW, r0 = r / TW;
-            const bool rows_full = rg * RPI + RPI <= Y;
-            const size_t row0 = ((size_t)z * Y + rg * RPI + r0) * X + col;
+            const bool rows_full = rg * RPI + RPI <= YSN;
+            const size_t row0 = ((size_t)z * YSN + rg * RPI + r0) * X + col;
             for (int u = x_lo + BW - 1; u >= x_lo; u--) {
                 if (act && u <= x_hi) {
                     const int d = u - cur.es;
@@ -428,7 +429,7 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
                         const int *tg = tile_g + r0 * (TW + 1) + col, *tc = tile_c + r0 * (TW + 1) + col;
 #pragma unroll
                         for (int k = 0; k < TW; k++) {        // RPI / (RPI / TW) = TW rows per thread
-                            if (rows_full || rg * RPI + r0 + k * (RPI / TW) < Y) {
+                            if (rows_full || rg * RPI + r0 + k * (RPI / TW) < YSN) {
                                 pg[(size_t)k * (RPI / TW) * X] = tg[k * (RPI / TW) * (TW + 1)];
                                 pc[(size_t)k * (RPI / TW) * X] = tc[k * (RPI / TW) * (TW + 1)];
                             }
@@ -453,7 +454,7 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
 {
     extern __shared__ int zs_smem[];
     __shared__ int s_item;
-    const int X = m.X, Y = m.Y, Z = m.Z;
+    const int X = m.X, Z = m.Z;
     const int ns = __ldg(n_slices);
     if (ns * 4 <= Z) return;                             // sparse regime: k_edt_zsweep
     const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW;
@@ -462,8 +463,8 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
     S.stH = zs_smem; S.stB = S.stH + NB * CAP * 32; S.meta = S.stB + NB * CAP * 32;
     S.CAP = CAP; S.r = lane;
     const int XG = (X + 31) / 32;
-    const int n_items = Y * XG;
-    const size_t slice = (size_t)X * Y;
+    const int n_items = m.ysn * XG;                      // rows of this map only; the arrays are [Z][ysn][X]
+    const size_t slice = (size_t)X * m.ysn;
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
@@ -522,19 +523,20 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4)
+template <int WARPS_PER_CTA>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
              int XG, int banded_dense)
 {
-    __shared__ int ring[WARPS_PER_CTA][2 * RING * 32];
+    extern __shared__ int zs_ring[];   // [WARPS_PER_CTA][2 * RING * 32]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * WARPS_PER_CTA + wid;
     LaneStack st;
-    st.sh = &ring[wid][lane]; st.sb = &ring[wid][RING * 32 + lane];
+    st.sh = zs_ring + wid * 2 * RING * 32 + lane; st.sb = st.sh + RING * 32;
     st.g = scratch + (size_t)gwarp * L * 32 + lane;
     const int X = m.X, Z = m.Z, S = m.max_width;
-    const size_t slice = (size_t)X * m.Y;
+    const size_t slice = (size_t)X * m.ysn;            // the arrays are [Z][ysn][X]: a slab of the rows, or all of them
     const int ns = __ldg(n_slices);
     if (ns * 4 > Z && banded_dense) return;   // dense regime: k_edt_zsweep_banded does the work
     // A CTA takes WARPS_PER_CTA adjacent 32-wide x groups of one row y at a time and its warps walk z in lockstep (one
@@ -554,6 +556,8 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         if (item >= n_items) break;
         const int y = item / XG8, xg = (item - y * XG8) * WARPS_PER_CTA + wid;
         const int x = xg * 32 + lane;
+        // (a ragged last group of the row, xg >= XG, runs the same code with valid = false on column 0 of the row: one barrier
+        // site for all warps of the CTA)
         const bool valid = xg < XG && x < X;
         const size_t base = (size_t)y * X + (valid ? x : 0);
         if (ns == 0) {   // no obstacle anywhere: every voxel "sees nothing" (D5)
@@ -561,10 +565,6 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
                 m.aux[base + (size_t)u * slice] = S * S;
                 m.coc_aux[base + (size_t)u * slice] = x | (INV_Y << 11) | (u << 22);
             }
-            continue;
-        }
-        if (xg >= XG) {   // ragged last group of the row: keep the barrier count of the lockstep loop below
-            if (lockstep) for (int u = Z - 1; u >= 0; u--) __syncthreads();
             continue;
         }
         int q = -1;
@@ -628,21 +628,35 @@ int gie_edt_prepare(gie_locmap *lm)
 {
     const LocDev &m = lm->d;
     int WY = (m.Y + 31) / 32;
+    const size_t slab_voxels = (size_t)m.Z * m.ysn * m.X;   // == N for a whole map
     GIE_CUDA_CHECK(cudaMalloc(&lm->ytab, (size_t)m.Z * WY * m.X * 8));
-    GIE_CUDA_CHECK(cudaMalloc(&lm->g2, (size_t)m.N * 4));
-    GIE_CUDA_CHECK(cudaMalloc(&lm->cxy, (size_t)m.N * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&lm->g2, slab_voxels * 4));
+    GIE_CUDA_CHECK(cudaMalloc(&lm->cxy, slab_voxels * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->col_list, (size_t)m.Z * m.X * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->edt_meta, (size_t)(2 * m.Z + 8) * 4));   // n_cols[Z], slice_list[Z], n_slices
     int L = m.X > m.Z ? m.X : m.Z;
-    int n_items = max(m.Z * WY, m.Y * ((m.X + 31) / 32));
-    int ctas = lm->num_sms * 4;
+    // serial z sweep: WARPS_PER_CTA adjacent x groups of one row per CTA (the width of the contiguous run a lockstep z step
+    // writes: 128 B x warps per array); 32 warps per SM in all shapes.  GIE_ZS_WPC overrides (measurement switch).
+    int wpc = 8;
+    if (getenv("GIE_ZS_WPC")) { int v = atoi(getenv("GIE_ZS_WPC")); if (v == 8 || v == 16 || v == 32) wpc = v; }
+    while (wpc > 8 && wpc * 32 > 2 * m.X) wpc >>= 1;   // no wider than the row
+    lm->zs_wpc = wpc;
+    const int WARPS_PER_CTA = wpc;
+    int n_items = m.ysn * ((m.X + 31) / 32);
+    int ctas = lm->num_sms * (32 / wpc);
     int need = (n_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (need < ctas) ctas = need;   // small volumes: no idle persistent CTAs
     lm->edt_ctas = ctas;
+    {
+        const int ring_bytes = wpc * 2 * RING * 32 * (int)sizeof(int);
+        if (wpc == 32) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+        else if (wpc == 16) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+        else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
+    }
     // x sweep: one CTA per (slice, RPI rows) item; bands of ~32 columns, one band per warp (RPI = 32) or two (RPI = 16, the
     // only shape whose stacks fit shared memory for X > 512).  GIE_XS_RPI overrides the choice (measurement switch).
     {
-        int rpi = m.X <= 512 ? 32 : 16;
+        int rpi = 16;   // measured faster than 32 at 512^3 in both regimes (two CTAs per SM instead of one; profiles/)
         if (getenv("GIE_XS_RPI")) { int v = atoi(getenv("GIE_XS_RPI")); if (v == 16 || (v == 32 && m.X <= 512)) rpi = v; }
         const int per_warp = 32 / rpi;
         int nwarps = std::min(16, (m.X + 31) / 32);
@@ -659,7 +673,7 @@ int gie_edt_prepare(gie_locmap *lm)
         if (rpi == 32) GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<32>, x.threads, x.smem));
         else GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<16>, x.threads, x.smem));
         if (xs_per_sm < 1) { gie_set_error("x sweep does not fit on an SM"); return GIE_ERR_CUDA; }
-        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.Y + rpi - 1) / rpi));
+        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.ysn + rpi - 1) / rpi));
     }
     // z sweep, dense regime: one band per warp; only when the stacks of a whole z column fit shared memory (Z <= ~880)
     {
@@ -670,13 +684,13 @@ int gie_edt_prepare(gie_locmap *lm)
         zb.smem = (size_t)(2 * zb.NB * zb.CAP * 32 + zb.NB * 32) * 4;
         int dev_max = 0;
         GIE_CUDA_CHECK(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, lm->device));
-        lm->zs_banded = zb.smem <= (size_t)dev_max && !getenv("GIE_ZS_NO_BANDED");
+        lm->zs_banded = zb.smem <= (size_t)dev_max && getenv("GIE_ZS_BANDED") != nullptr;   // off by default: measured slower than the serial sweep (profiles/)
         if (lm->zs_banded) {
             GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep_banded, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zb.smem));
             int per_sm = 1;
             GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_edt_zsweep_banded, zb.threads, zb.smem));
             if (per_sm < 1) lm->zs_banded = false;
-            lm->zs_ctas = std::min(lm->num_sms * std::max(per_sm, 1), m.Y * ((m.X + 31) / 32));
+            lm->zs_ctas = std::min(lm->num_sms * std::max(per_sm, 1), m.ysn * ((m.X + 31) / 32));
         }
     }
     lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
@@ -691,10 +705,10 @@ static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, 
     const BandCfg cfg{ x.NB, x.CAP, x.BW };
     if (x.rpi == 32)
         k_edt_xsweep<32><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0);
+                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
     else
         k_edt_xsweep<16><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0);
+                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
 }
 
 // dense regime first (returns at once when few slices hold obstacles), then the write-ordered serial sweep (returns at once in
@@ -703,15 +717,19 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
 {
     const int XG = (m.X + 31) / 32;
     const int L = m.X > m.Z ? m.X : m.Z;
+    const int wpc = lm->zs_wpc;
+    const size_t ring_bytes = (size_t)wpc * 2 * RING * 32 * sizeof(int);
+    const int n_items = m.ysn * ((XG + wpc - 1) / wpc);
     if (lm->zs_banded) {
         const BandCfg cfg{ lm->zs.NB, lm->zs.CAP, lm->zs.BW };
         k_edt_zsweep_banded<<<lm->zs_ctas, lm->zs.threads, lm->zs.smem, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, cfg,
                                                                                      lm->work_counters + 2);
         lm->launches++;
     }
-    k_edt_zsweep<<<lm->edt_ctas, WARPS_PER_CTA * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
-                                                                      lm->work_counters + 1, m.Y * ((XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA), XG,
-                                                                      lm->zs_banded ? 1 : 0);
+#define GIE_ZS_LAUNCH(W) k_edt_zsweep<W><<<lm->edt_ctas, W * 32, ring_bytes, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, \
+        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0)
+    if (wpc == 32) GIE_ZS_LAUNCH(32); else if (wpc == 16) GIE_ZS_LAUNCH(16); else GIE_ZS_LAUNCH(8);
+#undef GIE_ZS_LAUNCH
     lm->launches++;
 }
 
@@ -739,6 +757,64 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
     launch_zsweep(lm, m, slice_list, n_slices);
+    lm->launches += 1;
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
+// ---- volumes sharded over GPUs -----------------------------------------------------------------------------
+// The map that owns glb_type runs the y pass for the whole volume (gie_launch_edt_pack) and hands ytab / col_list / meta to
+// the slab maps, which run the x and z sweeps on their rows (gie_launch_edt_slab).  For a peer GPU only the planes of the
+// obstacle-bearing slices travel: k_edt_compact gathers them into [n_slices][...] buffers (the sweeps never read the others).
+namespace {
+__global__ void __launch_bounds__(256) k_edt_compact(const unsigned long long *__restrict__ ytab, const int *__restrict__ col_list,
+                                                     const int *__restrict__ slice_list, const int *__restrict__ n_slices, int WY, int X,
+                                                     unsigned long long *__restrict__ ytab_c, int *__restrict__ col_c)
+{
+    const int ns = __ldg(n_slices);
+    const size_t plane = (size_t)WY * X;
+    for (int zi = blockIdx.y; zi < ns; zi += gridDim.y) {
+        const int z = __ldg(&slice_list[zi]);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x)
+            ytab_c[zi * plane + i] = ytab[z * plane + i];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < X; i += gridDim.x * blockDim.x) col_c[(size_t)zi * X + i] = col_list[(size_t)z * X + i];
+    }
+}
+}  // namespace
+
+int gie_launch_edt_pack(gie_locmap *lm, unsigned long long *ytab_compact, int *col_compact)
+{
+    const LocDev &m = lm->d;
+    const int WY = (m.Y + 31) / 32;
+    int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
+    StageTimer t(lm, GIE_ST_EDT_PACK);
+    launch_ybits(lm, WY);
+    k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
+    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    lm->launches += 3;
+    if (ytab_compact && col_compact) {
+        k_edt_compact<<<dim3(lm->num_sms, 8), 256, 0, lm->stream>>>(lm->ytab, lm->col_list, slice_list, n_slices, WY, m.X, ytab_compact, col_compact);
+        lm->launches++;
+    }
+    GIE_CUDA_CHECK(cudaGetLastError());
+    return GIE_OK;
+}
+
+int gie_launch_edt_slab(gie_locmap *lm, int max_width)
+{
+    LocDev m = lm->d;
+    if (max_width > 0) m.max_width = max_width;
+    const int WY = (m.Y + 31) / 32;
+    int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
+    GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
+    {
+        StageTimer t(lm, GIE_ST_EDT_X);
+        launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
+    }
+    {
+        StageTimer t(lm, GIE_ST_EDT_Z);
+        launch_zsweep(lm, m, slice_list, n_slices);
+    }
     lm->launches += 1;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;

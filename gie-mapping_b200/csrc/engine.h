@@ -23,10 +23,19 @@ struct gie_locmap {
     int edt_ctas = 0;                     // persistent grid of the z sweep
     int xs_ctas = 0;                      // persistent grid of the x sweep
     XsLaunch xs;
+    bool edt_compact = false;             // ytab / col_list hold only the obstacle-bearing slices, in slice_list order (slab map fed by a peer)
+    bool slab_only = false;               // a slab map of a sharded volume: batch-EDT arrays for rows [ys0, ys0 + ysn) only
+    bool edt_inputs_aliased = false;      // ytab / col_list / edt_meta belong to another map on this device
+    void *ipc_opened[16]{};               // peer slab arrays mapped through CUDA IPC (closed on destroy)
+    int n_ipc_opened = 0;
     XsLaunch zs;                          // banded z sweep (dense regime)
     bool zs_banded = false;
+    int zs_wpc = 8;                       // warps per CTA of the serial z sweep
     int zs_ctas = 0;
     int *work_counters = nullptr;         // device: [4]
+    // ray-cast scratch: per-ray checkpoints, step counts and stop indices (ogm.cu)
+    void *ray_scratch = nullptr;
+    size_t ray_scratch_bytes = 0;
     // staging for *_host entry points
     float *stage_dev = nullptr;
     size_t stage_bytes = 0;
@@ -35,6 +44,7 @@ struct gie_locmap {
     cudaEvent_t ev[GIE_ST_COUNT][2]{};
     bool ev_valid[GIE_ST_COUNT]{};
     long long launches = 0;
+    bool glb_type_foreign = false;        // glb_type was overwritten from outside (test hook): the next merge clears all of it
     gie_hashmap *hm = nullptr;
 };
 
@@ -62,6 +72,10 @@ struct gie_hashmap {
     int wave_ctas = 0;
     int *merge_list = nullptr;    // table indices of the touched or allocated blocks that intersect the volume (per OGM merge)
     int *merge_count = nullptr;
+    int *prev_list = nullptr;     // the other buffer of the pair: swapped with merge_list every merge (see k_clear_prev_blocks)
+    int *prev_count = nullptr;
+    bool prev_valid = false;
+    int3 prev_pvt{}, prev_tab_org{};
     int *blk_list = nullptr;      // table indices of the allocated blocks that intersect the local volume (per merge)
     int *blk_count = nullptr;
     int merge_epoch = 0;          // merges done so far; the seed mark of m.wave_layer (memset to 0 at creation)
@@ -114,6 +128,8 @@ int gie_edt_prepare(gie_locmap *lm);
 int gie_launch_batch_edt(gie_locmap *lm);
 int gie_launch_edt_xy(gie_locmap *lm);
 int gie_launch_edt_z(gie_locmap *lm, int max_width_override);
+int gie_launch_edt_pack(gie_locmap *lm, unsigned long long *ytab_compact, int *col_compact);
+int gie_launch_edt_slab(gie_locmap *lm, int max_width);
 // wave.cu
 int gie_wave_prepare(gie_hashmap *hm);
 int gie_launch_merge(gie_hashmap *hm, int map_ct, int display_glb_edt);

@@ -113,6 +113,26 @@ __global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, 
     }
 }
 
+// glb_type must read UNKNOWN wherever no block exists.  The only voxels that can hold anything else are those of the blocks
+// the PREVIOUS merge visited (k_merge_ogm writes the voxels of listed blocks; the frontier marks land inside them too), at
+// the positions they had under the previous pivot — so those are cleared instead of the whole volume (134 MB per frame at
+// 512^3, 1 GB at 1024^3, against a few MB here).  One CTA pass per listed block, 2 voxels per thread.
+__global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_pvt, int3 tab_org, int3 tab_dim, const int *__restrict__ list,
+                                                           const int *__restrict__ count)
+{
+    const int n = __ldcg(count);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const int ti = __ldcg(&list[b]);
+        const int3 k = make_int3(ti % tab_dim.x, (ti / tab_dim.x) % tab_dim.y, ti / (tab_dim.x * tab_dim.y)) + tab_org;
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int v = threadIdx.x + 256 * u;
+            const int3 c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - prev_pvt;
+            if (gie_inside_loc(m, c)) m.glb_type[gie_lidx(m, c)] = GIE_VOX_UNKNOWN;
+        }
+    }
+}
+
 template <bool PNTCLD>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
                                                    const int *__restrict__ list, const int *__restrict__ count)
@@ -286,8 +306,18 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     gie_locmap *lm = hm->lm;
     StageTimer t(lm, GIE_ST_HASH_MERGE);
     const int entries = (int)hm->tab_entries;
+    // UNKNOWN wherever no block exists: clear what the previous merge may have written (the whole array only the first time
+    // and after a test upload), then swap the lists
+    if (hm->prev_valid && !lm->glb_type_foreign) {
+        k_clear_prev_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(lm->d, hm->prev_pvt, hm->prev_tab_org, hm->d.tab_dim, hm->merge_list,
+                                                                     hm->merge_count);
+        lm->launches++;
+    } else GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));
+    lm->glb_type_foreign = false;
+    std::swap(hm->merge_list, hm->prev_list);
+    std::swap(hm->merge_count, hm->prev_count);
+    hm->prev_valid = true; hm->prev_pvt = lm->d.pvt; hm->prev_tab_org = hm->d.tab_org;
     GIE_CUDA_CHECK(cudaMemsetAsync(hm->merge_count, 0, sizeof(int), lm->stream));
-    GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));   // UNKNOWN wherever no block exists
     k_list_merge_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, hm->merge_list,
                                                                                            hm->merge_count);
     const int grid = lm->num_sms * 16;

@@ -55,101 +55,166 @@ __global__ void k_pc_register(LocDev m, HashDev h, const float *__restrict__ pts
 
 // freeLocObs (pntcld_raycast.cu:67-80) + RAY::rayCastLoc (ray_cast.h:57-144)
 //
-// Every ray starts at the sensor, so the voxels around the origin are decremented by all ~64 k rays: tens of thousands of
-// same-address atomics that serialise in one L2 slice.  Each CTA therefore accumulates the decrements that fall into a
-// WIN^3 window around the origin voxel in shared memory and flushes the window once at the end (sums commute, the result
-// is identical); decrements outside the window go straight to global memory.
+// One thread per ray, as in the reference, leaves a B200 with ~14 warps per SM, each a chain of a few hundred dependent
+// steps (DDA step -> load of the voxel's type, which decides whether the ray stops -> decrement): 170 us at 6 active warps
+// per SM.  The walk itself is pure arithmetic, so it is split off:
+//   k_pc_walk  : thread = ray.  Runs the DDA without touching memory — the same float operations in the same order as
+//                ray_cast.h:104-143, so every visited voxel is the reference's — and checkpoints its state every RAY_SEG steps.
+//   k_pc_scan  : thread = (ray, segment).  Replays the segment from its checkpoint, loads the types of its voxels (RAY_SEG
+//                independent loads) and records the first OCCUPIED one: the ray stops there (clearRayLoc returns false).
+//   k_pc_apply : thread = (ray, segment).  Replays again and decrements every in-volume voxel before the stop.
+// ~20x the threads, every load and atomic independent of the others; the visited set and the counts are unchanged.
+// Every ray starts at the sensor, so the voxels around the origin are decremented by all rays: the CTAs of the first segment
+// accumulate the decrements that fall into a WIN^3 window around the origin voxel in shared memory and flush the window once
+// (sums commute, the result is identical).
 constexpr int RAY_WIN = 16;
-__global__ void __launch_bounds__(128) k_pc_free(LocDev m, HashDev h, const float *__restrict__ pts, int n, float max_length)
+constexpr int RAY_SEG = 32;
+struct RaySetup {
+    float3 p0, p1;
+    int3 p0i, p1i;
+    float len, tdx, tdy, tdz, tmx, tmy, tmz;
+    int sx, sy, sz;
+};
+// ray_cast.h:57-103, evaluated as written
+__device__ __forceinline__ void ray_setup(const LocDev &m, const float *__restrict__ pts, int i, RaySetup &r)
+{
+    r.p0 = m.origin;
+    r.p0i = pos2coord(m, r.p0);
+    float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    r.p1 = se3_apply(m.L2G, p);
+    r.p1i = pos2coord(m, r.p1);
+    float dx = r.p1.x - r.p0.x, dy = r.p1.y - r.p0.y, dz = r.p1.z - r.p0.z;
+    r.len = sqrtf(dx * dx + dy * dy + dz * dz);
+    dx = dx / r.len; dy = dy / r.len; dz = dz / r.len;
+    r.sx = dx > 0.0f ? 1 : (dx < 0.0f ? -1 : 0);
+    r.sy = dy > 0.0f ? 1 : (dy < 0.0f ? -1 : 0);
+    r.sz = dz > 0.0f ? 1 : (dz < 0.0f ? -1 : 0);
+    r.tmx = FLT_MAX; r.tmy = FLT_MAX; r.tmz = FLT_MAX; r.tdx = FLT_MAX; r.tdy = FLT_MAX; r.tdz = FLT_MAX;
+    if (r.sx != 0) { float b = (float)r.p0i.x * m.w + (float)r.sx * m.w * 0.5f; r.tmx = (b - r.p0.x) / dx; r.tdx = m.w / fabsf(dx); }
+    if (r.sy != 0) { float b = (float)r.p0i.y * m.w + (float)r.sy * m.w * 0.5f; r.tmy = (b - r.p0.y) / dy; r.tdy = m.w / fabsf(dy); }
+    if (r.sz != 0) { float b = (float)r.p0i.z * m.w + (float)r.sz * m.w * 0.5f; r.tmz = (b - r.p0.z) / dz; r.tdz = m.w / fabsf(dz); }
+}
+// one DDA step: the comparison tree of ray_cast.h:107-114, reproduced literally
+__device__ __forceinline__ void ray_step(const RaySetup &r, int3 &cur, float &tmx, float &tmy, float &tmz)
+{
+    if (tmx < tmy) {
+        if (tmx < tmz) { cur.x += r.sx; tmx += r.tdx; } else { cur.z += r.sz; tmz += r.tdz; }
+    } else {
+        if (tmy < tmz) { cur.y += r.sy; tmy += r.tdy; } else { cur.z += r.sz; tmz += r.tdz; }
+    }
+}
+struct RayCk { float tmx, tmy, tmz; int x, y, z; };   // state before step s * RAY_SEG
+
+__global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const float *__restrict__ pts, int n, float max_length, int max_segs,
+                                                 RayCk *__restrict__ ck, int *__restrict__ nsteps, int *__restrict__ stop)
+{
+    __shared__ int origin_dec;
+    if (threadIdx.x == 0) origin_dec = 0;
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    RaySetup r;
+    if (i < n) {
+        ray_setup(m, pts, i, r);
+        // first `opr` on the origin voxel (ray_cast.h:70-72; clearRayLoc pntcld_raycast.cu:9-18): one decrement per ray
+        const int3 loc = r.p0i - m.pvt;
+        if (gie_inside_loc(m, loc) && m.inst_type[gie_lidx(m, loc)] != GIE_VOX_OCCUPIED) atomicAdd(&origin_dec, 1);
+        int steps = 0;
+        if (!eq3(r.p0i, r.p1i)) {
+            int3 cur = r.p0i;
+            float tmx = r.tmx, tmy = r.tmy, tmz = r.tmz;
+            const int cap = max_segs * RAY_SEG;
+            for (;;) {
+                if ((steps & (RAY_SEG - 1)) == 0) ck[(size_t)(steps / RAY_SEG) * n + i] = RayCk{ tmx, tmy, tmz, cur.x, cur.y, cur.z };
+                ray_step(r, cur, tmx, tmy, tmz);
+                steps++;
+                const float d = fminf(fminf(tmx, tmy), tmz);
+                if (eq3(cur, r.p1i) || d > max_length || d > r.len || steps >= cap) break;
+            }
+        }
+        nsteps[i] = steps;
+        stop[i] = steps;   // no OCCUPIED voxel met yet: the whole walk counts
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && origin_dec) {
+        const int3 p0i = pos2coord(m, m.origin);
+        const int3 loc = p0i - m.pvt;
+        atomicAdd(&m.ray_count[gie_lidx(m, loc)], -origin_dec);
+        gie_touch_block(h, p0i);
+    }
+}
+
+// thread = (ray, segment); CTAs are segment-major so that all threads of a CTA work on the same segment index
+__global__ void __launch_bounds__(128) k_pc_scan(LocDev m, const float *__restrict__ pts, int n, int max_segs, const RayCk *__restrict__ ck,
+                                                 const int *__restrict__ nsteps, int *__restrict__ stop)
+{
+    const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int total = __ldg(&nsteps[i]), first = seg * RAY_SEG;
+    if (first >= total) return;
+    RaySetup r;
+    ray_setup(m, pts, i, r);
+    const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
+    int3 cur = make_int3(c.x, c.y, c.z);
+    float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
+    const int cnt = min(RAY_SEG, total - first);
+    int8_t t[RAY_SEG];
+#pragma unroll
+    for (int j = 0; j < RAY_SEG; j++) {
+        t[j] = GIE_VOX_UNKNOWN;
+        if (j < cnt) {
+            ray_step(r, cur, tmx, tmy, tmz);
+            const int3 loc = cur - m.pvt;
+            if (gie_inside_loc(m, loc)) t[j] = m.inst_type[gie_lidx(m, loc)];
+        }
+    }
+    int hit = RAY_SEG;
+#pragma unroll
+    for (int j = RAY_SEG - 1; j >= 0; j--) if (t[j] == GIE_VOX_OCCUPIED) hit = j;
+    if (hit < cnt) atomicMin(&stop[i], first + hit);
+}
+
+__global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, const float *__restrict__ pts, int n, int max_segs,
+                                                  const RayCk *__restrict__ ck, const int *__restrict__ stop)
 {
     __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
-    for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) win[k] = 0;
-    __syncthreads();
-    const float3 p0 = m.origin;
-    const int3 p0i = pos2coord(m, p0);
+    const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool use_win = seg == 0;                                  // uniform in the CTA
+    const int3 p0i = pos2coord(m, m.origin);
     const int3 worg = p0i - make_int3(RAY_WIN / 2, RAY_WIN / 2, RAY_WIN / 2);   // global coords of window cell (0,0,0)
-    // decrement of an in-volume voxel given its GLOBAL coords
-    int last_ti = -1;
-    auto dec = [&](int3 g, int id) {
-        int ti = gie_tab_index(h, g);
-        if (ti != last_ti) { h.touched[ti] = 1; last_ti = ti; }
-        int3 q = g - worg;
-        if ((unsigned)q.x < RAY_WIN && (unsigned)q.y < RAY_WIN && (unsigned)q.z < RAY_WIN) atomicAdd(&win[(q.z * RAY_WIN + q.y) * RAY_WIN + q.x], -1);
-        else atomicAdd(&m.ray_count[id], -1);   // result unused -> RED
-    };
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool active = i < n;
-    int3 p1i = p0i;
-    float3 p1 = p0;
-    if (active) {
-        float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
-        p1 = se3_apply(m.L2G, p);
-        p1i = pos2coord(m, p1);
-        // first `opr` on the origin voxel (ray_cast.h:70-72; clearRayLoc pntcld_raycast.cu:9-18)
-        int3 loc = p0i - m.pvt;
-        if (gie_inside_loc(m, loc)) {
-            int id = gie_lidx(m, loc);
-            if (m.inst_type[id] != GIE_VOX_OCCUPIED) dec(p0i, id);
-        }
-        if (eq3(p0i, p1i)) active = false;
+    if (use_win) {
+        for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) win[k] = 0;
+        __syncthreads();
     }
-    if (active) {
-        float dx = p1.x - p0.x, dy = p1.y - p0.y, dz = p1.z - p0.z;
-        float len = sqrtf(dx * dx + dy * dy + dz * dz);
-        dx = dx / len; dy = dy / len; dz = dz / len;
-        int sx = dx > 0.0f ? 1 : (dx < 0.0f ? -1 : 0);
-        int sy = dy > 0.0f ? 1 : (dy < 0.0f ? -1 : 0);
-        int sz = dz > 0.0f ? 1 : (dz < 0.0f ? -1 : 0);
-        float tmx = FLT_MAX, tmy = FLT_MAX, tmz = FLT_MAX, tdx = FLT_MAX, tdy = FLT_MAX, tdz = FLT_MAX;
-        if (sx != 0) { float b = (float)p0i.x * m.w + (float)sx * m.w * 0.5f; tmx = (b - p0.x) / dx; tdx = m.w / fabsf(dx); }
-        if (sy != 0) { float b = (float)p0i.y * m.w + (float)sy * m.w * 0.5f; tmy = (b - p0.y) / dy; tdy = m.w / fabsf(dy); }
-        if (sz != 0) { float b = (float)p0i.z * m.w + (float)sz * m.w * 0.5f; tmz = (b - p0.z) / dz; tdz = m.w / fabsf(dz); }
-        int3 cur = p0i;
-        // The walk itself is pure arithmetic; what made a step slow was the dependent load of inst_type that decides whether
-        // the ray stops.  inst_type is read-only in this kernel, so the DDA runs K steps ahead, the K loads are issued
-        // together, and the decisions (stop at the first OCCUPIED voxel, otherwise decrement) are then applied in order —
-        // same voxels, same order, same float operations as the one-step-at-a-time loop of ray_cast.h:104-143.
-        constexpr int K = 8;
-        for (;;) {
-            int ids[K];
-            int3 gs[K];
-            int nsteps = 0;
-            bool finished = false;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (finished) { ids[j] = -1; gs[j] = cur; continue; }
-                // comparison tree of ray_cast.h:107-114, reproduced literally
-                if (tmx < tmy) {
-                    if (tmx < tmz) { cur.x += sx; tmx += tdx; } else { cur.z += sz; tmz += tdz; }
-                } else {
-                    if (tmy < tmz) { cur.y += sy; tmy += tdy; } else { cur.z += sz; tmz += tdz; }
-                }
-                int3 loc = cur - m.pvt;
-                ids[j] = gie_inside_loc(m, loc) ? gie_lidx(m, loc) : -1;
-                gs[j] = cur;
-                nsteps = j + 1;
-                float d = fminf(fminf(tmx, tmy), tmz);
-                finished = eq3(cur, p1i) || d > max_length || d > len;
-            }
-            int8_t t[K];
-#pragma unroll
-            for (int j = 0; j < K; j++) t[j] = (j < nsteps && ids[j] >= 0) ? m.inst_type[ids[j]] : (int8_t)GIE_VOX_UNKNOWN;
-            bool hit = false;
-#pragma unroll
-            for (int j = 0; j < K; j++) {
-                if (hit || j >= nsteps || ids[j] < 0) continue;
-                if (t[j] == GIE_VOX_OCCUPIED) hit = true;            // clearRayLoc returns false: the ray stops here
-                else dec(gs[j], ids[j]);
-            }
-            if (hit || finished) break;
+    const int first = seg * RAY_SEG;
+    const int last = i < n ? __ldg(&stop[i]) : 0;                    // steps [0, last) are decremented
+    if (i < n && first < last) {
+        RaySetup r;
+        ray_setup(m, pts, i, r);
+        const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
+        int3 cur = make_int3(c.x, c.y, c.z);
+        float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
+        const int cnt = min(RAY_SEG, last - first);
+        int last_ti = -1;
+        for (int j = 0; j < cnt; j++) {
+            ray_step(r, cur, tmx, tmy, tmz);
+            const int3 loc = cur - m.pvt;
+            if (!gie_inside_loc(m, loc)) continue;                   // the walk continues outside the volume (ray_cast.h:116-121)
+            const int ti = gie_tab_index(h, cur);
+            if (ti != last_ti) { h.touched[ti] = 1; last_ti = ti; }
+            const int3 q = cur - worg;
+            if (use_win && (unsigned)q.x < RAY_WIN && (unsigned)q.y < RAY_WIN && (unsigned)q.z < RAY_WIN)
+                atomicAdd(&win[(q.z * RAY_WIN + q.y) * RAY_WIN + q.x], -1);
+            else atomicAdd(&m.ray_count[gie_lidx(m, loc)], -1);      // result unused -> RED
         }
     }
-    __syncthreads();
-    for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) {
-        int v = win[k];
-        if (v == 0) continue;
-        int3 loc = worg + make_int3(k % RAY_WIN, (k / RAY_WIN) % RAY_WIN, k / (RAY_WIN * RAY_WIN)) - m.pvt;
-        atomicAdd(&m.ray_count[gie_lidx(m, loc)], v);   // only in-volume voxels were accumulated
+    if (use_win) {
+        __syncthreads();
+        for (int k = threadIdx.x; k < RAY_WIN * RAY_WIN * RAY_WIN; k += blockDim.x) {
+            const int v = win[k];
+            if (v == 0) continue;
+            const int3 loc = worg + make_int3(k % RAY_WIN, (k / RAY_WIN) % RAY_WIN, k / (RAY_WIN * RAY_WIN)) - m.pvt;
+            atomicAdd(&m.ray_count[gie_lidx(m, loc)], v);            // only in-volume voxels were accumulated
+        }
     }
 }
 
@@ -316,8 +381,23 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
         k_pc_register<<<blocks, 256, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n);
         // pntcld_raycast.cu:79: 0.707f*loc_map._local_size.x*loc_map._voxel_width
         float max_len = 0.707f * (float)lm->d.X * lm->d.w;
-        k_pc_free<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len);
-        lm->launches += 2;
+        // a walk crosses at most (|dx| + |dy| + |dz|) <= sqrt(3) voxel borders per voxel of length: bound on the segments of a ray
+        const int max_steps = (int)(0.707f * (float)lm->d.X * 1.7320508f) + 8;
+        const int max_segs = (max_steps + RAY_SEG - 1) / RAY_SEG;
+        const size_t need = (size_t)n * max_segs * sizeof(RayCk) + (size_t)n * 2 * sizeof(int) + 256;
+        if (lm->ray_scratch_bytes < need) {
+            if (lm->ray_scratch) { GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream)); GIE_CUDA_CHECK(cudaFree(lm->ray_scratch)); lm->ray_scratch = nullptr; }
+            GIE_CUDA_CHECK(cudaMalloc(&lm->ray_scratch, need));
+            lm->ray_scratch_bytes = need;
+        }
+        RayCk *ck = (RayCk *)lm->ray_scratch;
+        int *nsteps = (int *)((char *)lm->ray_scratch + (((size_t)n * max_segs * sizeof(RayCk) + 127) & ~(size_t)127));
+        int *stop = nsteps + n;
+        const dim3 grid2((n + 127) / 128, max_segs);
+        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, nsteps, stop);
+        k_pc_scan<<<grid2, 128, 0, lm->stream>>>(lm->d, pts_dev, n, max_segs, ck, nsteps, stop);
+        k_pc_apply<<<grid2, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_segs, ck, stop);
+        lm->launches += 4;
     }
     if (fmp) {
         int r = 0;

@@ -159,8 +159,9 @@ __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const 
             const int id = gie_lidx(m, c);
             if (m.glb_type[id] == GIE_VOX_UNKNOWN) continue;
             const size_t vi = (size_t)blk * 512 + v;
-            const int dist_new = m.aux[id], dist_old = h.dist_sq[vi];
-            int3 coc_new = gie_id2wr((uint32_t)m.coc_aux[id]);   // same 11/11/10 packing, local coords
+            int32_t *const paux = gie_aux_ptr(m, c);
+            const int dist_new = *paux, dist_old = h.dist_sq[vi];
+            int3 coc_new = gie_id2wr((uint32_t)*gie_coc_aux_ptr(m, c));   // same 11/11/10 packing, local coords
             int aux = dist_new, pdist;
             uint32_t pid;
             bool have_id = false;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const 
                 if (!have_id) pid = gie_pair_id(m.pair[id]);     // stale id word
             } else { pdist = aux; pid = gie_wr2id(wr); }
             m.pair[id] = gie_mk_pair(pdist, pid);
-            if (aux != dist_new) m.aux[id] = aux;
+            if (aux != dist_new) *paux = aux;
         }
     }
 }
@@ -348,7 +349,7 @@ __device__ void waveA_phase1(const LocDev &m, const HashDev &h, const WaveDev &w
             if (eq3(ncoc, lcoc)) continue;
             bool raised = false;
             int3 ncb = ncoc - m.pvt;
-            if (gie_inside_loc(m, ncb) && m.aux[gie_lidx(m, ncb)] != 0) {
+            if (gie_inside_loc(m, ncb) && *gie_aux_ptr(m, ncb) != 0) {
                 unsigned long long cand = GIE_RAISE_TAG | gie_mk_pair(sqd3(lcoc, ng), gie_wr2id(cur_wr));
                 unsigned long long old = __ldcg(&h.pair[ni]);
                 for (;;) {
@@ -446,7 +447,7 @@ __device__ void waveB_phase2(const LocDev &m, const HashDev &h, const WaveDev &w
                     old[d] = atomicMin(&h.pair[ni[d]], key[d]);
                 } else {
                     nid[d] = gie_lidx(m, nb);
-                    if (m.aux[nid[d]] > cand) { kind[d] = 2; atomicMin(&m.pair[nid[d]], key[d]); }
+                    if (*gie_aux_ptr(m, nb) > cand) { kind[d] = 2; atomicMin(&m.pair[nid[d]], key[d]); }
                 }
             }
             int col[6];

@@ -79,6 +79,10 @@ def load_library():
         "gie_hashmap_wave_stats": [p, p], "gie_profile_enable": [p, i], "gie_profile_last": [p, p],
         "gie_launch_count": [p, C.POINTER(C.c_longlong)], "gie_warmup": [],
         "gie_hashmap_check_edt": [p, i, p, p],
+        "gie_locmap_create_slab": [C.POINTER(p), i, i, i, i, i], "gie_slab_alias_inputs": [p, p],
+        "gie_slab_input_buffers": [p, C.POINTER(p), C.POINTER(C.c_size_t), C.POINTER(p), C.POINTER(C.c_size_t), C.POINTER(p), C.POINTER(C.c_size_t)],
+        "gie_slab_set_compact": [p, i], "gie_edt_pack": [p, p, p], "gie_edt_slab_sweeps": [p, i], "gie_ipc_export": [p, p],
+        "gie_locmap_attach_slabs": [p, i, i, p, p, p, p],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)

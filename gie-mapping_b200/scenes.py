@@ -173,6 +173,12 @@ def make_config(name, local_size=None):
                     ogm_min_h=-10.0, ogm_max_h=10.0, occupancy_threshold=180, bucket_max=400000, block_max=600000,
                     lidar=dict(rings=32, az=2048, elev_min=-22.5, elev_max=22.5, max_range=50.0),
                     world=dict(extent=40.0, height=6.0, n_boxes=200, ceiling=False), start=(-12.0, -3.0, 1.5))
+    if name == "cfg5":   # multi-GPU: OS-64 131 072 pts, 1024 x 1024 x 1016 @ 0.1 m (Z <= 1022: 10-bit z of the coc codec), cutoff 5 m
+        size = local_size or (1024, 1024, 1016)
+        return dict(name=name, sensor="pointcloud", voxel_width=0.1, local_size=size, cutoff_grids_sq=2500, fast_mode=False,
+                    ogm_min_h=-10.0, ogm_max_h=10.0, occupancy_threshold=180, bucket_max=800000, block_max=1200000,
+                    lidar=dict(rings=64, az=2048, elev_min=-22.5, elev_max=22.5, max_range=60.0),
+                    world=dict(extent=60.0, height=8.0, n_boxes=400, ceiling=False), start=(-12.0, -3.0, 1.5))
     raise KeyError(name)
 
 

@@ -174,6 +174,31 @@ int gie_edt_batch_update(gie_locmap *lm);
  * local_batch.h:44), 0 = this map's own. */
 int gie_edt_xy_sweeps(gie_locmap *lm);
 int gie_edt_z_sweep(gie_locmap *lm, int max_width_override);
+/* ---- one volume sharded over several GPUs (no reference counterpart) -------------------------------------------
+ * The dense half of the frame — the x and z sweeps of the batch EDT, which write 8 B per voxel of the volume — is cut into
+ * slabs of rows y, one per GPU; the sparse half (ray cast, hash merge, wavefronts) stays with the map that owns the hashed
+ * global map and reads the batch-EDT result out of the slabs, its own or a peer GPU's (CUDA IPC mapping over NVLink).
+ *   gie_locmap_create_slab  : a map that holds only the batch-EDT arrays of rows [row0, row0 + rows) (row0 % 32 == 0)
+ *   gie_slab_alias_inputs   : same device as the owner map: read its ytab / column lists directly
+ *   gie_slab_input_buffers  : other device: the buffers to receive them into (e.g. with an NCCL broadcast);
+ *   gie_slab_set_compact    :   compact = only the planes of the obstacle-bearing slices were sent, in slice order
+ *   gie_edt_pack            : owner map: the y pass of the whole volume (EDTphase1 as bit words + links, column and slice lists);
+ *                             optionally gathers the planes of the obstacle-bearing slices into contiguous send buffers
+ *   gie_edt_slab_sweeps     : EDTphase2 + EDTphase3 on the slab's rows; max_width = X+Y+Z of the whole volume (0 = own)
+ *   gie_ipc_export          : CUDA IPC handle (64 bytes) of a slab's output array, for the owner process
+ *   gie_locmap_attach_slabs : owner map: use these slabs as the batch-EDT result (device pointers for slabs of this process, IPC
+ *                             handles [64 * n_slabs] for the others, pointer NULL); frees its own whole-volume copies */
+int gie_locmap_create_slab(gie_locmap **out, int size_x, int size_y, int size_z, int row0, int rows);
+int gie_slab_alias_inputs(gie_locmap *slab, gie_locmap *owner);
+int gie_slab_input_buffers(gie_locmap *slab, void **ytab_dev, size_t *ytab_bytes, void **col_list_dev, size_t *col_bytes, void **meta_dev,
+                           size_t *meta_bytes);
+int gie_slab_set_compact(gie_locmap *slab, int compact);
+int gie_edt_pack(gie_locmap *lm, void *ytab_compact_dev, void *col_compact_dev);
+int gie_edt_slab_sweeps(gie_locmap *slab, int max_width);
+int gie_ipc_export(void *dev_ptr, unsigned char handle64[64]);
+int gie_locmap_attach_slabs(gie_locmap *lm, int n_slabs, int slab_rows, void *const *aux_dev, void *const *coc_dev,
+                            const unsigned char *aux_handles, const unsigned char *coc_handles);
+
 /* GlbHashMap::mergeNewObsv (glb_hash_map.cu:146-207).  display_glb_edt: record blocks whose distances changed
  * (wave_core.cuh:128-134,250-256; unify_helper.cuh:510-520) for gie_hashmap_stream_changed. */
 int gie_hashmap_merge_new_obsv(gie_hashmap *hm, int map_ct, int display_glb_edt);

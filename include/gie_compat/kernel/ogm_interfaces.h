@@ -2,7 +2,17 @@
 // src/kernel/hokuyo/hokuyo_interfaces.h:9-13, src/kernel/vlp16/vlp16_interface.h:12-16,
 // src/kernel/realsense/realsense_interfaces.h:9-13).  Same namespaces, names and argument lists; the sensor data pointer
 // is a DEVICE pointer as in the reference.  `VB_keys_loc_D` is accepted and ignored.
+//
+// The reference's src/*_map_maker.cpp include "kernel/<sensor>/<sensor>_interfaces.h" with quotes, which the compiler resolves
+// NEXT TO THE INCLUDING FILE first, i.e. to the reference's own declaration-only headers under src/kernel/.  A build that
+// keeps those .cpp files therefore needs these four functions as linkable symbols: compile gie_compat_kernels.cpp (this
+// directory's parent), which includes this header with GIE_COMPAT_EMIT_KERNEL_SYMBOLS defined.
 #pragma once
+#ifdef GIE_COMPAT_EMIT_KERNEL_SYMBOLS
+#define GIE_KERNEL_ENTRY
+#else
+#define GIE_KERNEL_ENTRY inline
+#endif
 #include "cuda_toolkit/projection.h"
 #include "cuda_toolkit/occupancy/sensor_params.h"
 #include "map_structure/local_batch.h"
@@ -16,7 +26,7 @@ inline void use_projection(LocMap *m, const Projection &p)
 }  // namespace gie
 
 namespace PNTCLD_RAYCAST {
-inline void localOGMKernels(LocMap *loc_map, float3 *pnt_cld, Projection proj, PntcldParam param, int3 * /*VB_keys_loc_D*/,
+GIE_KERNEL_ENTRY void localOGMKernels(LocMap *loc_map, float3 *pnt_cld, Projection proj, PntcldParam param, int3 * /*VB_keys_loc_D*/,
                             int /*time*/, bool for_motion_planner, int rbt_r2_grids)
 {
     gie::use_projection(loc_map, proj);
@@ -24,7 +34,7 @@ inline void localOGMKernels(LocMap *loc_map, float3 *pnt_cld, Projection proj, P
 }
 }
 namespace HOKUYO_FAST {
-inline void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projection proj, ScanParam param, int3 *, bool for_motion_planner,
+GIE_KERNEL_ENTRY void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projection proj, ScanParam param, int3 *, bool for_motion_planner,
                             int rbt_r2_grids)
 {
     gie::use_projection(loc_map, proj);
@@ -33,7 +43,7 @@ inline void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projec
 }
 }
 namespace VLP_FAST {
-inline void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projection proj, MulScanParam param, int3 *, bool for_motion_planner,
+GIE_KERNEL_ENTRY void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projection proj, MulScanParam param, int3 *, bool for_motion_planner,
                             int rbt_r2_grids)
 {
     gie::use_projection(loc_map, proj);
@@ -42,7 +52,7 @@ inline void localOGMKernels(LocMap *loc_map, SCAN_DEPTH_TPYE *detph_data, Projec
 }
 }
 namespace REALSENSE_FAST {
-inline void localOGMKernels(LocMap *loc_map, REALSENSE_DEPTH_TPYE *detph_data, Projection proj, CamParam param, int3 *, bool for_motion_planner,
+GIE_KERNEL_ENTRY void localOGMKernels(LocMap *loc_map, REALSENSE_DEPTH_TPYE *detph_data, Projection proj, CamParam param, int3 *, bool for_motion_planner,
                             int rbt_r2_grids)
 {
     gie::use_projection(loc_map, proj);

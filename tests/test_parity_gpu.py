@@ -718,3 +718,47 @@ def test_full_size_parity(gie, oracle, name, nframes):
         om.close()
         if ref_path and os.path.exists(ref_path):
             os.remove(ref_path)
+
+
+def test_reference_map_makers_run(gie):
+    """The program built by tests/test_host_cpu.py::test_reference_map_makers_compile_unchanged — the reference's OWN unmodified
+    src/*_map_maker.cpp linked against include/gie_compat and the C ABI — integrates one 2-D scan and one PointCloud2 message
+    through HokuyoMapMaker / PntcldMapMaker; the occupancy it produces must equal what the Python mirror produces from the same
+    payloads."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(gie.library_path()), "host", "_build", "test_reference_map_makers")
+    if not os.path.exists(exe):
+        pytest.skip("built only where /root/reference is present (CPU suite of the build container)")
+    res = subprocess.run([exe, "--run"], capture_output=True, text=True)
+    assert res.returncode == 0 and "reference map makers run OK" in res.stdout, res.stdout + res.stderr
+    got = {l.split()[0]: int(l.split()[1]) for l in res.stdout.splitlines() if l.split()[0] in ("scan2d", "pointcloud")}
+
+    def fnv(a):
+        h = 1469598103934665603
+        for b in a.astype(np.uint8).ravel().tolist():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return h
+
+    q, t = np.array([1, 0, 0, 0], np.float32), np.array([0.3, -0.2, 1.5], np.float32)
+    lm = gie.LocMap(0.2, (64, 64, 32), 180, -10.0, 10.0, 100, True)
+    hm = gie.GlbHashMap(lm, 4000, 12000)
+    try:
+        lm.set_pose(q, t)
+        hm.ogm_scan2d(np.full(1081, 3.0, np.float32), float(np.float32(0.25 * 3.14159265 / 180.0)), float(np.float32(-135.0 * 3.14159265 / 180.0)))
+        hm.updateHashOGM(False, 1)
+        assert fnv(lm.download(gie.ARR_GLB_TYPE)) == got["scan2d"]
+    finally:
+        hm.close(); lm.close()
+    lm = gie.LocMap(0.1, (64, 64, 32), 180, -10.0, 10.0, 64, False)
+    hm = gie.GlbHashMap(lm, 4000, 12000)
+    try:
+        lm.set_pose(q, t)
+        i = np.arange(2000)
+        pts = np.stack([np.float32(-2.0) + np.float32(0.002) * i.astype(np.float32), np.full(2000, 1.5, np.float32),
+                        np.float32(0.25) + np.float32(0.05) * (i % 7).astype(np.float32)], 1).astype(np.float32)
+        hm.ogm_pointcloud(pts)
+        hm.updateHashOGM(True, 1)
+        assert fnv(lm.download(gie.ARR_GLB_TYPE)) == got["pointcloud"]
+    finally:
+        hm.close(); lm.close()
