@@ -713,6 +713,16 @@ int gie_hashmap_export_blocks(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel 
     return GIE_OK;
 }
 
+int gie_hashmap_device_view(gie_hashmap *hm, gie_device_view *out)
+{
+    if (!hm || !out) return GIE_ERR_INVALID_ARG;
+    const HashDev &h = hm->d;
+    out->keys = h.keys; out->vals = h.vals; out->cap_mask = h.cap_mask; out->block_max = h.block_max; out->block_count = h.block_count;
+    out->occ_val = h.occ_val; out->vox_type = (const signed char *)h.vox_type; out->update_ct = h.update_ct; out->coc_glb = h.coc_glb;
+    out->dist_sq = h.dist_sq; out->wave_layer = h.wave_layer; out->pair = h.pair;
+    return GIE_OK;
+}
+
 int gie_hashmap_num_changed(gie_hashmap *hm, int *n)
 {
     if (!hm || !n) return GIE_ERR_INVALID_ARG;

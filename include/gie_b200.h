@@ -216,6 +216,27 @@ int gie_sync(gie_hashmap *hm);
  * keys_host = int[3*n], voxels_host = gie_glbvoxel[512*n] with voxel index (x&7)*64+(y&7)*8+(z&7) */
 int gie_hashmap_num_blocks(gie_hashmap *hm, int *n);
 int gie_hashmap_export_blocks(gie_hashmap *hm, int32_t *keys_host, gie_glbvoxel *voxels_host, int max_blocks);
+/* Device-side view of the global map for GPU consumers (README.md:163-170: "Each voxel can be retrieved by using device
+ * function get_VB_key() and get_voxID_in_VB()").  Raw device pointers of the engine's open-addressing block table and of its
+ * FIELD-MAJOR voxel pools (index = block * 512 + (z&7)*64 + (y&7)*8 + (x&7)); include/gie_compat/par_wave/gie_device_view.cuh
+ * holds the matching __device__ accessors (gie_dv_find_block, gie_dv_voxel -> GlbVoxel).  Valid until the map is destroyed;
+ * reads must be ordered after the engine's work on its stream. */
+typedef struct gie_device_view {
+    const unsigned long long *keys;   /* packed block key (3 x 21 bit) or ~0 */
+    const int32_t *vals;              /* block index of the key slot */
+    uint32_t cap_mask;
+    int32_t block_max;
+    const int32_t *block_count;
+    const unsigned char *occ_val;
+    const signed char *vox_type;
+    const int32_t *update_ct;
+    const unsigned long long *coc_glb; /* 21 bits per axis, biased by 2^20 */
+    const int32_t *dist_sq;
+    const int32_t *wave_layer;
+    const unsigned long long *pair;    /* (dist_sq << 32) | wave-range coc id */
+} gie_device_view;
+int gie_hashmap_device_view(gie_hashmap *hm, gie_device_view *out);
+
 /* frontier sizes / BFS levels of the last merge: {fA, fB, fC, levelsA, levelsB, levelsC, fB_after_A, fC_after_B} */
 int gie_hashmap_wave_stats(gie_hashmap *hm, int64_t out8[8]);
 

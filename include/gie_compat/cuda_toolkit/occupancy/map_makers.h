@@ -126,12 +126,20 @@ public:
 #ifdef GIE_COMPAT_WITH_ROS
     void updateLocalOGM(const Projection &proj, const sensor_msgs::PointCloud2ConstPtr &msg, int3 *keys, const int time, bool fmp, int r2)
     {
-        int ox = -1, oy = -1, orr = -1;
+        // field lookup with the reference's datatype checks (convertPyntCld, vlp16_map_maker.cpp:81-109): FLOAT32 = 7, UINT16 = 4
+        int ox = -1, oy = -1, oi = -1, orr = -1;
         for (const auto &f : msg->fields) {
-            if (f.name == "x") ox = (int)f.offset; else if (f.name == "y") oy = (int)f.offset; else if (f.name == "ring") orr = (int)f.offset;
+            if (f.datatype == 7) {
+                if (f.name == "x") ox = (int)f.offset; else if (f.name == "y") oy = (int)f.offset; else if (f.name == "intensity") oi = (int)f.offset;
+            } else if (f.datatype == 4 && f.name == "ring") orr = (int)f.offset;
         }
-        if (ox < 0 || oy < 0 || orr < 0) return;   // the reference builds no scan lines either (:113)
-        updateLocalOGM(proj, msg->data.data(), (int)(msg->width * msg->height), (int)msg->point_step, ox, oy, orr, keys, time, fmp, r2);
+        // The reference bins only when x, y and ring exist AND x sits at offset 0, y at 4 and the intensity / ring offsets are
+        // multiples of 4 (:111-121; it indexes the point as a float array); otherwise its scan lines stay all-INFINITY and the OGM
+        // kernel still runs on them (:52-70), which marks the whole field of view FREE.  Same here: zero points give an
+        // all-INFINITY range image.
+        const bool binned = ox >= 0 && oy >= 0 && orr >= 0 && ox == 0 && oy == 4 && (oi % 4 == 0) && (orr % 4 == 0);
+        const int n = binned ? (int)(msg->width * msg->height) : 0;
+        updateLocalOGM(proj, msg->data.data(), n, (int)msg->point_step, binned ? ox : 0, binned ? oy : 0, binned ? orr : 0, keys, time, fmp, r2);
     }
 #endif
 private:

@@ -1,6 +1,12 @@
 // Stand-in for include/par_wave/voxmap_utils.cuh: the voxel-block layout and key helpers that the reference documents for
-// planners reading the streamed global map (README.md:163-170).  Host-side only.
+// planners reading the streamed global map (README.md:163-170).  get_VB_key / get_voxID_in_VB are __host__ __device__ when
+// compiled by nvcc, as in the reference; the device-side access to the engine's pools is in gie_device_view.cuh.
 #pragma once
+#ifdef __CUDACC__
+#define GIE_HD __host__ __device__ __forceinline__
+#else
+#define GIE_HD inline
+#endif
 #include <cstddef>
 #include <cstdint>
 #include "map_structure/local_batch.h"
@@ -38,11 +44,11 @@ struct BlockHasher {
 };
 
 // block key of a global voxel coordinate: floor(c / 8) per axis
-inline int3 get_VB_key(const int3 &c) { return make_int3(c.x >> 3, c.y >> 3, c.z >> 3); }
+GIE_HD int3 get_VB_key(const int3 &c) { return make_int3(c.x >> 3, c.y >> 3, c.z >> 3); }
 // voxel index inside its block, reference order (x slowest, z fastest)
-inline int get_voxID_in_VB(const int3 &c) { return (c.x & 7) * 64 + (c.y & 7) * 8 + (c.z & 7); }
-inline int3 reconstruct_vox_crd(const int3 &blk_offset, const int &idx)
+GIE_HD int get_voxID_in_VB(const int3 &c) { return (c.x & 7) * 64 + (c.y & 7) * 8 + (c.z & 7); }
+GIE_HD int3 reconstruct_vox_crd(const int3 &blk_offset, const int &idx)
 {
     return make_int3(blk_offset.x + ((idx >> 6) & 7), blk_offset.y + ((idx >> 3) & 7), blk_offset.z + (idx & 7));
 }
-inline bool invalid_blk_key(const int3 &k) { return k.x >= EMPTY_VALUE || k.y >= EMPTY_VALUE || k.z >= EMPTY_VALUE; }
+GIE_HD bool invalid_blk_key(const int3 &k) { return k.x >= EMPTY_VALUE || k.y >= EMPTY_VALUE || k.z >= EMPTY_VALUE; }

@@ -181,3 +181,16 @@ def test_reference_map_makers_compile_unchanged(tmp_path):
     os.makedirs(out, exist_ok=True)
     import shutil
     shutil.copy(exe, os.path.join(out, "test_reference_map_makers"))
+
+
+def test_device_view_planner_builds(tmp_path):
+    """A GPU consumer built together with the mapper (README.md:163-170): tests/cpp/test_device_view.cu compiles with nvcc for
+    sm_100a against include/gie_compat (get_VB_key / get_voxID_in_VB as __host__ __device__, gie_device_view.cuh) and links with
+    the C ABI library.  The GPU suite runs it (tests/test_parity_gpu.py::test_device_view_planner_runs)."""
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "gie-mapping_b200", "csrc")])
+    out = os.path.join(ROOT, "gie-mapping_b200", "host", "_build")
+    os.makedirs(out, exist_ok=True)
+    libdir = os.path.join(ROOT, "gie-mapping_b200")
+    subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", f"-I{ROOT}/include/gie_compat",
+                           f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", "test_device_view.cu"), "-o", os.path.join(out, "test_device_view"),
+                           f"-L{libdir}", "-lgie_b200", "-Xlinker", "-rpath,$ORIGIN/../.."])

@@ -762,3 +762,15 @@ def test_reference_map_makers_run(gie):
         assert fnv(lm.download(gie.ARR_GLB_TYPE)) == got["pointcloud"]
     finally:
         hm.close(); lm.close()
+
+
+def test_device_view_planner_runs(gie):
+    """The GPU "planner" of tests/cpp/test_device_view.cu: 20 000 global voxels read from a kernel through gie_device_view and
+    the reference's device helpers equal the host mirror of the same blocks, field by field."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(gie.library_path()), "host", "_build", "test_device_view")
+    if not os.path.exists(exe):
+        pytest.skip("built by the CPU suite (tests/test_host_cpu.py::test_device_view_planner_builds)")
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0 and "device view OK" in res.stdout, res.stdout + res.stderr
