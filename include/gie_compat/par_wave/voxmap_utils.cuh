@@ -51,4 +51,7 @@ GIE_HD int3 reconstruct_vox_crd(const int3 &blk_offset, const int &idx)
 {
     return make_int3(blk_offset.x + ((idx >> 6) & 7), blk_offset.y + ((idx >> 3) & 7), blk_offset.z + (idx & 7));
 }
+// voxmap_utils.cuh:161-172
+GIE_HD bool invalid_dist_glb(const int dist) { return dist < 0 || dist >= 900000; }
+GIE_HD bool invalid_coc_glb(const int3 coc) { return coc.x > 900000 || coc.y > 900000 || coc.z > 900000; }
 GIE_HD bool invalid_blk_key(const int3 &k) { return k.x >= EMPTY_VALUE || k.y >= EMPTY_VALUE || k.z >= EMPTY_VALUE; }

@@ -1,0 +1,2 @@
+#pragma once
+#include <pcl/point_cloud.h>

@@ -1,4 +1,5 @@
 #pragma once
 #include <cstdint>
 #include <string>
-namespace std_msgs { struct Header { uint32_t seq = 0; double stamp = 0; std::string frame_id; }; }
+#include <ros/time.h>
+namespace std_msgs { struct Header { uint32_t seq = 0; ros::Time stamp; std::string frame_id; }; }

@@ -194,3 +194,40 @@ def test_device_view_planner_builds(tmp_path):
     subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-w", f"-I{ROOT}/include/gie_compat",
                            f"-I{ROOT}/include", os.path.join(ROOT, "tests", "cpp", "test_device_view.cu"), "-o", os.path.join(out, "test_device_view"),
                            f"-L{libdir}", "-lgie_b200", "-Xlinker", "-rpath,$ORIGIN/../.."])
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="the reference checkout is only present in the build container")
+def test_reference_node_compiles_unchanged(tmp_path):
+    """The whole host side of the reference — src/main.cpp, src/volumetric_mapper.cpp and the four src/*_map_maker.cpp, plus its
+    node-level headers volumetric_mapper.h / parameters.h / simple_logger.h / gt_checker.h — compiled UNMODIFIED against
+    include/gie_compat and linked with the C ABI library into the node binary.  ROS, tf, message_filters, Eigen and PCL are not
+    installed in this image: tests/cpp/node_stubs holds compile-only stand-ins for the names the node uses.
+    The four node-level headers are copied to a scratch directory first: `#include "..."` resolves next to the including file
+    before any -I path, so inside the reference's include/ tree they would pick up the reference's own local_batch.h etc.
+    (INTEGRATION.md §1 says the same to a maintainer)."""
+    import shutil
+    subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "gie-mapping_b200", "csrc")])
+    inc = os.path.join(ROOT, "include")
+    node_inc, node_src = tmp_path / "inc", tmp_path / "src"
+    node_inc.mkdir(); node_src.mkdir()
+    for h in ["volumetric_mapper.h", "parameters.h", "simple_logger.h", "gt_checker.h"]:
+        shutil.copy(os.path.join("/root/reference/include", h), node_inc / h)
+    srcs = ["main.cpp", "volumetric_mapper.cpp", "hokuyo_map_maker.cpp", "realsense_map_maker.cpp", "pntcld_map_maker.cpp", "vlp16_map_maker.cpp"]
+    for s in srcs:
+        shutil.copy(os.path.join(REF_SRC, s), node_src / s)
+    flags = ["-std=c++17", "-O1", "-w", "-DGIE_COMPAT_REFERENCE_MAPMAKERS", "-DGIE_COMPAT_WITH_TF", f"-I{inc}/gie_compat", f"-I{inc}",
+             "-I/usr/local/cuda/include", f"-I{ROOT}/tests/cpp/node_stubs", f"-I{ROOT}/tests/cpp/ros_stubs", f"-I{node_inc}"]
+    objs = []
+    for s in srcs + [os.path.join(inc, "gie_compat", "gie_compat_kernels.cpp")]:
+        src = s if os.path.isabs(s) else str(node_src / s)
+        obj = str(tmp_path / (os.path.basename(s) + ".o"))
+        subprocess.check_call(["g++", *flags, "-c", src, "-o", obj])
+        objs.append(obj)
+    # the map makers reach the reference's own kernel interface headers through quoted includes next to their .cpp: provide them
+    libdir = os.path.join(ROOT, "gie-mapping_b200")
+    out = os.path.join(libdir, "host", "_build")
+    os.makedirs(out, exist_ok=True)
+    exe = os.path.join(out, "gie_node_stub_ros")
+    subprocess.check_call(["g++", *objs, "-o", exe, f"-L{libdir}", "-lgie_b200", "-L/usr/local/cuda/lib64", "-lcudart", f"-Wl,-rpath,{libdir}",
+                           "-Wl,-rpath,/usr/local/cuda/lib64"])
+    assert os.path.getsize(exe) > 100000
