@@ -527,7 +527,7 @@ template <int WARPS_PER_CTA>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
-             int XG, int banded_dense)
+             int XG, int banded_dense, int sync_mask)
 {
     extern __shared__ int zs_ring[];   // [WARPS_PER_CTA][2 * RING * 32]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -596,7 +596,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         int32_t *pa = m.aux + base + (size_t)(Z - 1) * slice;
         int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
         for (int u = Z - 1; u >= 0; u--) {
-            if (lockstep) __syncthreads();
+            if (lockstep && (u & sync_mask) == 0) __syncthreads();
             if (valid) {
                 const int d = u - top.s;
                 __stcs(pa, d * d + top.h);
@@ -641,6 +641,9 @@ int gie_edt_prepare(gie_locmap *lm)
     if (getenv("GIE_ZS_WPC")) { int v = atoi(getenv("GIE_ZS_WPC")); if (v == 8 || v == 16 || v == 32) wpc = v; }
     while (wpc > 8 && wpc * 32 > 2 * m.X) wpc >>= 1;   // no wider than the row
     lm->zs_wpc = wpc;
+    // lockstep barrier every (mask + 1) z steps; GIE_ZS_SYNC = 1, 2, 4, 8 ... (0 = never: mask of all ones never matches u >= 0 ... use a large power of two)
+    lm->zs_sync_mask = 0;
+    if (getenv("GIE_ZS_SYNC")) { int v = atoi(getenv("GIE_ZS_SYNC")); if (v == 0) lm->zs_sync_mask = (1 << 20) - 1; else if (v > 0 && (v & (v - 1)) == 0) lm->zs_sync_mask = v - 1; }
     const int WARPS_PER_CTA = wpc;
     int n_items = m.ysn * ((m.X + 31) / 32);
     int ctas = lm->num_sms * (32 / wpc);
@@ -727,7 +730,7 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
         lm->launches++;
     }
 #define GIE_ZS_LAUNCH(W) k_edt_zsweep<W><<<lm->edt_ctas, W * 32, ring_bytes, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, \
-        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0)
+        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0, lm->zs_sync_mask)
     if (wpc == 32) GIE_ZS_LAUNCH(32); else if (wpc == 16) GIE_ZS_LAUNCH(16); else GIE_ZS_LAUNCH(8);
 #undef GIE_ZS_LAUNCH
     lm->launches++;

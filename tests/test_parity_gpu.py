@@ -391,10 +391,8 @@ def test_cuda_engine_vs_reference_golden(gie, path):
                 exact_frames += 1
             else:
                 waves_seen = True
-                assert (t != rt).sum() <= 8, f"frame {k}: glb_type differs in {(t != rt).sum()} voxels"
-                assert (od[known] == rd[known]).mean() >= 0.95, f"frame {k}"
-                diff = (od - rd)[known & (od < 900000) & (rd < 900000)]
-                assert (diff < 0).sum() >= (diff > 0).sum(), f"frame {k}: reference closer more often"
+                assert (t != rt).sum() <= 2, f"frame {k}: glb_type differs in {(t != rt).sum()} voxels"
+                assert (od[known] == rd[known]).mean() >= 0.999, f"frame {k}: {(od[known] != rd[known]).sum()} distances differ"
         assert exact_frames >= 1
     finally:
         mp.close()
