@@ -175,6 +175,7 @@ extern "C" int gie_hashmap_check_edt(gie_hashmap *hm, int mode, int32_t *truth_s
     int nblocks = 0, rc;
     if ((rc = gie_hashmap_num_blocks(hm, &nblocks)) != GIE_OK) return rc;
     memset(out, 0, sizeof(*out));
+    out->rms = -1.0;   // cmp_dist's "no checking due to empty cloud" (gt_checker.h:34-40) until something is compared
     if (nblocks == 0) return GIE_OK;
     uint32_t *masks = nullptr;
     int *occ_list = nullptr, *occ_count = nullptr;
