@@ -214,10 +214,10 @@ __device__ __forceinline__ int bd_meta_pack(int lo, int hi1, int tf) { return lo
 template <int R>
 struct BandStacks {
     int *stH, *stB, *meta;
-    int CAP, r;
+    int sk, si, r;           // element (band k, entry i) of line r lives at k * sk + i * si + r
     __device__ __forceinline__ int &M(int k) const { return meta[k * R + r]; }
-    __device__ __forceinline__ int H(int k, int i) const { return stH[(k * CAP + i) * R + r]; }
-    __device__ __forceinline__ int B(int k, int i) const { return stB[(k * CAP + i) * R + r]; }
+    __device__ __forceinline__ int H(int k, int i) const { return stH[k * sk + i * si + r]; }
+    __device__ __forceinline__ int B(int k, int i) const { return stB[k * sk + i * si + r]; }
 };
 
 // one push of the sequential algorithm (EDTphase2/3 forward loops, local_edt_core.h:93-115 / :146-168) onto the stack of band
@@ -225,12 +225,13 @@ struct BandStacks {
 template <int R>
 __device__ __forceinline__ void band_push(const BandStacks<R> &S, int b, int u, int h_u, int extra, int L, int &q, int &ts, int &tt, int &th)
 {
-    int *myH = S.stH + (size_t)b * S.CAP * R + S.r, *myB = S.stB + (size_t)b * S.CAP * R + S.r;
+    int *myH = S.stH + b * S.sk + S.r, *myB = S.stB + b * S.sk + S.r;
+    const int si = S.si;
     while (q >= 0) {
         const int a = tt - ts, c = tt - u;
         if (a * a + th > c * c + h_u) {
             q--;
-            if (q >= 0) { const int bb = myB[q * R]; th = myH[q * R]; ts = bb & 0x3ff; tt = (bb >> 10) & 0x3ff; }
+            if (q >= 0) { const int bb = myB[q * si]; th = myH[q * si]; ts = bb & 0x3ff; tt = (bb >> 10) & 0x3ff; }
         } else break;
     }
     int w = 0;
@@ -238,8 +239,8 @@ __device__ __forceinline__ void band_push(const BandStacks<R> &S, int b, int u, 
     if (w < L) {
         q++;
         ts = u; tt = w; th = h_u;
-        myH[q * R] = h_u;
-        myB[q * R] = u | (w << 10) | extra;
+        myH[q * si] = h_u;
+        myB[q * si] = u | (w << 10) | extra;
     }
 }
 
@@ -331,46 +332,48 @@ struct EnvCursor {
 };
 
 // ---- x sweep (EDTphase2, local_edt_core.h:84-135) ---------------------------------------------------------------------
-// Work item = (obstacle-bearing slice z, RPI consecutive rows y); thread = (band of real columns, row).  The backward pass
-// emits through a [RPI][TW] shared-memory tile so that global stores run along x: the in-kernel transpose that replaces
-// cuTT's {1,0,2} permutation and its inverse.
-template <int RPI>
-__global__ void __launch_bounds__(512)
+// Work item = ONE row (obstacle-bearing slice z, row y), processed by ONE warp: lane = band.  The real columns of the slice are
+// cut into 32 bands of at most CAP = ceil(X / 32) candidates; every lane builds its band's envelope, the 32 envelopes are merged
+// in a tree of 5 rounds, and every lane walks its range of BW = ceil(X / 32) output positions.  All synchronisation is
+// __syncwarp: a first version with (band, row) threads spread over a 512-thread CTA spent two thirds of its stall samples at
+// the 8 CTA barriers of an item (profiles/r02_ncu_scene_xsweep_cta.txt).  Stacks are entry-major ([entry][band]: bank = lane).
+// The row is assembled in shared memory and stored with full 128-byte lines: the in-kernel transpose that replaces cuTT's
+// {1,0,2} permutation and its inverse.
+constexpr int XS_WARPS = 8;
+__global__ void __launch_bounds__(XS_WARPS * 32)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
-             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter, int compact)
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, int CAP, int *__restrict__ work_counter, int compact)
 {
-    constexpr int TW = RPI == 32 ? 16 : 8;               // tile width: a row segment of 64 / 32 bytes per store
     extern __shared__ int xs_smem[];
-    __shared__ int s_item;
-    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW;
+    constexpr int NB = 32;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int r = lane % RPI, b = wid * (32 / RPI) + lane / RPI;
-    BandStacks<RPI> S;
-    S.stH = xs_smem;                                     // [NB][CAP][RPI]  h
-    S.stB = S.stH + NB * CAP * RPI;                      // [NB][CAP][RPI]  s | t << 10 | cy << 20
-    S.meta = S.stB + NB * CAP * RPI;                     // [NB][RPI]
-    S.CAP = CAP; S.r = r;
-    int *tile_g = S.meta + NB * RPI + b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);   // [NB][2][RPI][TW + 1]
     const int X = m.X;
+    const int BW = CAP;                                  // output positions per lane
+    const int row_ints = X + NB;                         // row buffer, one pad word per band: index x + x / BW
+    const int per_warp = 2 * NB * CAP + NB + 2 * row_ints;
+    int *wsm = xs_smem + wid * per_warp;
+    BandStacks<1> S;
+    S.stH = wsm; S.stB = wsm + NB * CAP; S.meta = wsm + 2 * NB * CAP;
+    S.sk = 1; S.si = NB; S.r = 0;
+    int *row_g = S.meta + NB, *row_c = row_g + row_ints;
+    const int b = lane;
     const int YS0 = m.ys0, YSN = m.ysn;                  // rows of this map (a slab of a sharded volume, or all of them)
-    const int RG = (YSN + RPI - 1) / RPI;                // row groups per slice
-    const int n_items = __ldg(n_slices) * RG;
+    const int n_items = __ldg(n_slices) * YSN;
     for (;;) {
-        __syncthreads();   // the previous item's stacks and tiles are no longer read
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = s_item;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int zi = item / RG, rg = item - zi * RG;
+        const int zi = item / YSN, yl = item - zi * YSN;
         const int z = __ldg(&slice_list[zi]);
-        const int y = YS0 + rg * RPI + r;
+        const int y = YS0 + yl;
         const int wy = y >> 5, p = y & 31;               // ytab word and bit of this row
         const int zp = compact ? zi : z;                 // plane of ytab / col_list: compacted to the real slices when received from a peer
         const unsigned long long *trow = ytab + ((size_t)zp * WY + wy) * X;
         const int *cols = col_list + (size_t)zp * X;
         const int nc = __ldg(&n_cols[z]);
-        // ---- 1. forward pass over this band's real columns
+        // ---- 1. forward pass over this lane's band of the real columns
         {
             const int jb = (int)((long long)nc * b / NB), je = (int)((long long)nc * (b + 1) / NB);
             int q = -1, ts = 0, tt = 0, th = 0;
@@ -395,50 +398,41 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
                 }
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (j0 + k < je) band_push<RPI>(S, b, uu[k], gg[k], cc[k] << 20, X, q, ts, tt, th);
+                    if (j0 + k < je) band_push<1>(S, b, uu[k], gg[k], cc[k] << 20, X, q, ts, tt, th);
             }
-            S.M(b) = bd_meta_pack(0, q + 1, 0);
+            S.meta[b] = bd_meta_pack(0, q + 1, 0);
         }
         // ---- 2. pairwise merges: (0 <- 1), (2 <- 3), ... then (0..1 <- 2..3), ... until the row's envelope is described
+#pragma unroll
         for (int stride = 1; stride < NB; stride <<= 1) {
-            __syncthreads();
-            if ((b & (2 * stride - 1)) == 0 && b + stride < NB) band_merge<RPI>(S, b, stride, NB, X);
+            __syncwarp();
+            if ((b & (2 * stride - 1)) == 0) band_merge<1>(S, b, stride, NB, X);
         }
-        __syncthreads();
-        // ---- 3. backward pass (local_edt_core.h:116-134) over this band's x range, emitted through a RPI x TW tile
+        __syncwarp();
+        // ---- 3. backward pass (local_edt_core.h:116-134) over this lane's x range into the row buffers
         {
             const int x_lo = b * BW, x_hi = min(X, x_lo + BW) - 1;
-            const bool act = x_lo <= x_hi;
-            EnvCursor<RPI> cur{};
-            if (act) cur.seek(S, NB, x_hi);
-            // flush geometry: thread r stores column (r % TW) of rows r / TW, r / TW + RPI / TW, ...
-            const int col = r % TW, r0 = r / TW;
-            const bool rows_full = rg * RPI + RPI <= YSN;
-            const size_t row0 = ((size_t)z * YSN + rg * RPI + r0) * X + col;
-            for (int u = x_lo + BW - 1; u >= x_lo; u--) {
-                if (act && u <= x_hi) {
+            if (x_lo <= x_hi) {
+                EnvCursor<1> cur{};
+                cur.seek(S, NB, x_hi);
+                for (int u = x_hi; u >= x_lo; u--) {
                     const int d = u - cur.es;
-                    tile_g[r * (TW + 1) + (u & (TW - 1))] = d * d + cur.eh;
-                    tile_c[r * (TW + 1) + (u & (TW - 1))] = cur.es | ((cur.eb >> 20) << 16);
+                    row_g[u + b] = d * d + cur.eh;
+                    row_c[u + b] = cur.es | ((cur.eb >> 20) << 16);
                     if (u == cur.et && u > 0) cur.prev(S);
-                }
-                if ((u & (TW - 1)) == 0) {
-                    __syncwarp();
-                    if (act && u + col < X) {
-                        int32_t *pg = g2 + row0 + u, *pc = cxy + row0 + u;
-                        const int *tg = tile_g + r0 * (TW + 1) + col, *tc = tile_c + r0 * (TW + 1) + col;
-#pragma unroll
-                        for (int k = 0; k < TW; k++) {        // RPI / (RPI / TW) = TW rows per thread
-                            if (rows_full || rg * RPI + r0 + k * (RPI / TW) < YSN) {
-                                pg[(size_t)k * (RPI / TW) * X] = tg[k * (RPI / TW) * (TW + 1)];
-                                pc[(size_t)k * (RPI / TW) * X] = tc[k * (RPI / TW) * (TW + 1)];
-                            }
-                        }
-                    }
-                    __syncwarp();
                 }
             }
         }
+        __syncwarp();
+        {
+            int32_t *pg = g2 + ((size_t)z * YSN + yl) * X, *pc = cxy + ((size_t)z * YSN + yl) * X;
+            for (int xx = lane; xx < X; xx += 32) {
+                const int i = xx + xx / BW;
+                pg[xx] = row_g[i];
+                pc[xx] = row_c[i];
+            }
+        }
+        __syncwarp();   // the stacks and row buffers are free for the next item
     }
 }
 
@@ -461,7 +455,7 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
     const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
     BandStacks<32> S;
     S.stH = zs_smem; S.stB = S.stH + NB * CAP * 32; S.meta = S.stB + NB * CAP * 32;
-    S.CAP = CAP; S.r = lane;
+    S.sk = CAP * 32; S.si = 32; S.r = lane;
     const int XG = (X + 31) / 32;
     const int n_items = m.ysn * XG;                      // rows of this map only; the arrays are [Z][ysn][X]
     const size_t slice = (size_t)X * m.ysn;
@@ -527,7 +521,7 @@ template <int WARPS_PER_CTA>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
-             int XG, int banded_dense, int sync_mask)
+             int XG, int banded_dense)
 {
     extern __shared__ int zs_ring[];   // [WARPS_PER_CTA][2 * RING * 32]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -539,26 +533,18 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     const size_t slice = (size_t)X * m.ysn;            // the arrays are [Z][ysn][X]: a slab of the rows, or all of them
     const int ns = __ldg(n_slices);
     if (ns * 4 > Z && banded_dense) return;   // dense regime: k_edt_zsweep_banded does the work
-    // A CTA takes WARPS_PER_CTA adjacent 32-wide x groups of one row y at a time and its warps walk z in lockstep (one
-    // __syncthreads per z step), so that every step the CTA writes ONE contiguous run per output array (1 KB / 1 KB / 2 KB at
-    // 8 warps) instead of eight unrelated 128-byte lines at eight different depths: the sweep is bound by its 16 B/voxel of
-    // writes and DRAM page locality decides how fast those go.
-    // Lockstep only pays when the sweep is write-bound, i.e. when few slices hold obstacles; with obstacles in most slices the
-    // envelope work per step varies a lot between warps and the per-step barrier costs more than the locality gains.
-    __shared__ int s_item;
-    const bool lockstep = ns * 4 <= Z;
-    const int XG8 = (XG + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    // Work item = 32 consecutive x of one row y, one warp each, pulled from a counter per warp (no CTA-wide synchronisation).
+    // (Round 1 gave a CTA 8 adjacent x groups and walked z in lockstep for DRAM page locality; with two output arrays instead of
+    // three the barrier costs more than it gains — 0.32 vs 0.30 ms — and a synthetic kernel with this store pattern reaches
+    // 5.5-6.0 TB/s without any ordering, scratch/write_pattern.cu.)
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(work_counter, 1);
-        __syncthreads();
-        const int item = s_item;
+        int item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= n_items) break;
-        const int y = item / XG8, xg = (item - y * XG8) * WARPS_PER_CTA + wid;
+        const int y = item / XG, xg = item - y * XG;
         const int x = xg * 32 + lane;
-        // (a ragged last group of the row, xg >= XG, runs the same code with valid = false on column 0 of the row: one barrier
-        // site for all warps of the CTA)
-        const bool valid = xg < XG && x < X;
+        const bool valid = x < X;
         const size_t base = (size_t)y * X + (valid ? x : 0);
         if (ns == 0) {   // no obstacle anywhere: every voxel "sees nothing" (D5)
             for (int u = 0; u < Z && valid; u++) {
@@ -587,30 +573,30 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             int k = __ldg(&slice_list[j]);
             envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
         }
-        // backward (local_edt_core.h:169-192).  The coc word is constant along one envelope segment (one owner slice), so it
-        // is recomputed only when the owner changes; a z step is then d*d + h, two streaming stores and pointer bumps.
+        // backward (local_edt_core.h:169-192), one envelope segment (one owner slice) at a time: inside a segment the coc word
+        // and (s, h) are constant, so a z step is d*d + h, two streaming stores and one index bump (the first version tested
+        // `u == top.t` and bumped two 64-bit pointers every step: 23 instructions per step against ~9 here).
         // (_dist_id_pair is NOT written here: the reference leaves the pair of UNKNOWN voxels stale and the wavefronts relax
         // against those stale words, so only k_mark_blocks writes it, for known voxels — unify_helper.cuh:217-218.)
-        int c = __ldg(&cxy[base + (size_t)top.s * slice]);
-        int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
-        int32_t *pa = m.aux + base + (size_t)(Z - 1) * slice;
-        int32_t *pc = m.coc_aux + base + (size_t)(Z - 1) * slice;
-        for (int u = Z - 1; u >= 0; u--) {
-            if (lockstep && (u & sync_mask) == 0) __syncthreads();
+        size_t o = base + (size_t)(Z - 1) * slice;
+        int u = Z - 1;
+        for (;;) {
+            const int end = top.t, s_ = top.s, h_ = top.h;      // this entry owns z in [end, u]; the bottom entry starts at 0
             if (valid) {
-                const int d = u - top.s;
-                __stcs(pa, d * d + top.h);
-                __stcs(pc, coc_word);
-            }
-            pa -= slice; pc -= slice;
-            if (u == top.t) {
-                q--;
-                if (q >= 0) {
-                    top = st.get(q);
-                    c = __ldg(&cxy[base + (size_t)top.s * slice]);
-                    coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+                const int c = __ldg(&cxy[base + (size_t)s_ * slice]);
+                const int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (s_ << 22);
+#pragma unroll 4
+                for (int v = u; v >= end; v--) {
+                    const int d = v - s_;
+                    __stcs(m.aux + o, d * d + h_);
+                    __stcs(m.coc_aux + o, coc_word);
+                    o -= slice;
                 }
             }
+            u = end - 1;
+            if (u < 0) break;
+            q--;
+            top = st.get(q);
         }
     }
 }
@@ -641,9 +627,6 @@ int gie_edt_prepare(gie_locmap *lm)
     if (getenv("GIE_ZS_WPC")) { int v = atoi(getenv("GIE_ZS_WPC")); if (v == 8 || v == 16 || v == 32) wpc = v; }
     while (wpc > 8 && wpc * 32 > 2 * m.X) wpc >>= 1;   // no wider than the row
     lm->zs_wpc = wpc;
-    // lockstep barrier every (mask + 1) z steps; GIE_ZS_SYNC = 1, 2, 4, 8 ... (0 = never: mask of all ones never matches u >= 0 ... use a large power of two)
-    lm->zs_sync_mask = 0;
-    if (getenv("GIE_ZS_SYNC")) { int v = atoi(getenv("GIE_ZS_SYNC")); if (v == 0) lm->zs_sync_mask = (1 << 20) - 1; else if (v > 0 && (v & (v - 1)) == 0) lm->zs_sync_mask = v - 1; }
     const int WARPS_PER_CTA = wpc;
     int n_items = m.ysn * ((m.X + 31) / 32);
     int ctas = lm->num_sms * (32 / wpc);
@@ -656,27 +639,16 @@ int gie_edt_prepare(gie_locmap *lm)
         else if (wpc == 16) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
         else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
     }
-    // x sweep: one CTA per (slice, RPI rows) item; bands of ~32 columns, one band per warp (RPI = 32) or two (RPI = 16, the
-    // only shape whose stacks fit shared memory for X > 512).  GIE_XS_RPI overrides the choice (measurement switch).
+    // x sweep: one warp per row of an obstacle-bearing slice; persistent CTAs of XS_WARPS warps, as many as fit
     {
-        int rpi = 16;   // measured faster than 32 at 512^3 in both regimes (two CTAs per SM instead of one; profiles/)
-        if (getenv("GIE_XS_RPI")) { int v = atoi(getenv("GIE_XS_RPI")); if (v == 16 || (v == 32 && m.X <= 512)) rpi = v; }
-        const int per_warp = 32 / rpi;
-        int nwarps = std::min(16, (m.X + 31) / 32);
         XsLaunch &x = lm->xs;
-        x.rpi = rpi; x.threads = nwarps * 32;
-        x.NB = nwarps * per_warp;
-        const int TW = rpi == 32 ? 16 : 8;               // k_edt_xsweep's tile width
-        x.CAP = (m.X + x.NB - 1) / x.NB;
-        x.BW = ((m.X + x.NB - 1) / x.NB + TW - 1) / TW * TW;
-        x.smem = (size_t)(2 * x.NB * x.CAP * rpi + x.NB * rpi + x.NB * 2 * rpi * (TW + 1)) * 4;
-        if (rpi == 32) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
-        else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
+        x.NB = 32; x.CAP = (m.X + 31) / 32; x.BW = x.CAP; x.threads = XS_WARPS * 32;
+        x.smem = (size_t)XS_WARPS * (2 * 32 * x.CAP + 32 + 2 * (m.X + 32)) * 4;
+        GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
         int xs_per_sm = 1;
-        if (rpi == 32) GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<32>, x.threads, x.smem));
-        else GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep<16>, x.threads, x.smem));
+        GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep, x.threads, x.smem));
         if (xs_per_sm < 1) { gie_set_error("x sweep does not fit on an SM"); return GIE_ERR_CUDA; }
-        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.ysn + rpi - 1) / rpi));
+        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, (m.Z * m.ysn + XS_WARPS - 1) / XS_WARPS);
     }
     // z sweep, dense regime: one band per warp; only when the stacks of a whole z column fit shared memory (Z <= ~880)
     {
@@ -705,13 +677,8 @@ int gie_edt_prepare(gie_locmap *lm)
 static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, int *n_slices)
 {
     const XsLaunch &x = lm->xs;
-    const BandCfg cfg{ x.NB, x.CAP, x.BW };
-    if (x.rpi == 32)
-        k_edt_xsweep<32><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
-    else
-        k_edt_xsweep<16><<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices,
-                                                                        lm->g2, lm->cxy, cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
+    k_edt_xsweep<<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices, lm->g2, lm->cxy,
+                                                                x.CAP, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
 }
 
 // dense regime first (returns at once when few slices hold obstacles), then the write-ordered serial sweep (returns at once in
@@ -722,7 +689,7 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
     const int L = m.X > m.Z ? m.X : m.Z;
     const int wpc = lm->zs_wpc;
     const size_t ring_bytes = (size_t)wpc * 2 * RING * 32 * sizeof(int);
-    const int n_items = m.ysn * ((XG + wpc - 1) / wpc);
+    const int n_items = m.ysn * XG;
     if (lm->zs_banded) {
         const BandCfg cfg{ lm->zs.NB, lm->zs.CAP, lm->zs.BW };
         k_edt_zsweep_banded<<<lm->zs_ctas, lm->zs.threads, lm->zs.smem, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, cfg,
@@ -730,7 +697,7 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
         lm->launches++;
     }
 #define GIE_ZS_LAUNCH(W) k_edt_zsweep<W><<<lm->edt_ctas, W * 32, ring_bytes, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, \
-        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0, lm->zs_sync_mask)
+        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0)
     if (wpc == 32) GIE_ZS_LAUNCH(32); else if (wpc == 16) GIE_ZS_LAUNCH(16); else GIE_ZS_LAUNCH(8);
 #undef GIE_ZS_LAUNCH
     lm->launches++;
