@@ -332,107 +332,125 @@ struct EnvCursor {
 };
 
 // ---- x sweep (EDTphase2, local_edt_core.h:84-135) ---------------------------------------------------------------------
-// Work item = ONE row (obstacle-bearing slice z, row y), processed by ONE warp: lane = band.  The real columns of the slice are
-// cut into 32 bands of at most CAP = ceil(X / 32) candidates; every lane builds its band's envelope, the 32 envelopes are merged
-// in a tree of 5 rounds, and every lane walks its range of BW = ceil(X / 32) output positions.  All synchronisation is
-// __syncwarp: a first version with (band, row) threads spread over a 512-thread CTA spent two thirds of its stall samples at
-// the 8 CTA barriers of an item (profiles/r02_ncu_scene_xsweep_cta.txt).  Stacks are entry-major ([entry][band]: bank = lane).
-// The row is assembled in shared memory and stored with full 128-byte lines: the in-kernel transpose that replaces cuTT's
-// {1,0,2} permutation and its inverse.
-constexpr int XS_WARPS = 8;
-__global__ void __launch_bounds__(XS_WARPS * 32)
+// Work item = (obstacle-bearing slice z, 16 consecutive rows y); thread = (band of real columns, row), two bands per warp.
+//   0. the CTA stages the item's candidates once: column index and ytab entry of every real column of the slice, one coalesced
+//      gather (two dependent global loads per thread per item instead of two per candidate inside the scan);
+//   1-3. forward per band, tree of merges, backward per x range (see above).  The backward pass emits through a [16][8]
+//      shared-memory tile so that global stores run along x: the in-kernel transpose that replaces cuTT's {1,0,2} permutation
+//      and its inverse.
+// The next item's index is fetched while the current one is processed.  (A variant with one WARP per row — lane = band, no CTA
+// barrier at all — executed 2.9x the instructions: lanes of different bands diverge in every pop loop and a merge round keeps
+// 16, 8, 4, 2, 1 lanes busy; 0.28 ms against 0.20 for this shape, profiles/r02_edt_experiments.md.)
+constexpr int XS_RPI = 16, XS_TW = 8;
+__global__ void __launch_bounds__(512)
 k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, const int *__restrict__ col_list,
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
-             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, int CAP, int *__restrict__ work_counter, int compact)
+             int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter, int compact)
 {
+    constexpr int RPI = XS_RPI, TW = XS_TW;
     extern __shared__ int xs_smem[];
-    constexpr int NB = 32;
+    __shared__ int s_item[2];
+    const int NB = cfg.NB, CAP = cfg.CAP, BW = cfg.BW;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r = lane % RPI, b = wid * (32 / RPI) + lane / RPI;
     const int X = m.X;
-    const int BW = CAP;                                  // output positions per lane
-    const int row_ints = X + NB;                         // row buffer, one pad word per band: index x + x / BW
-    const int per_warp = 2 * NB * CAP + NB + 2 * row_ints;
-    int *wsm = xs_smem + wid * per_warp;
-    BandStacks<1> S;
-    S.stH = wsm; S.stB = wsm + NB * CAP; S.meta = wsm + 2 * NB * CAP;
-    S.sk = 1; S.si = NB; S.r = 0;
-    int *row_g = S.meta + NB, *row_c = row_g + row_ints;
-    const int b = lane;
+    BandStacks<RPI> S;
+    S.stH = xs_smem;                                     // [NB][CAP][RPI]  h
+    S.stB = S.stH + NB * CAP * RPI;                      // [NB][CAP][RPI]  s | t << 10 | cy << 20
+    S.meta = S.stB + NB * CAP * RPI;                     // [NB][RPI]
+    S.sk = CAP * RPI; S.si = RPI; S.r = r;
+    int *tile_g = S.meta + NB * RPI + b * 2 * RPI * (TW + 1), *tile_c = tile_g + RPI * (TW + 1);   // [NB][2][RPI][TW + 1]
+    int *cand_u = S.meta + NB * RPI + NB * 2 * RPI * (TW + 1);                                      // [X] column of candidate j
+    unsigned long long *cand_e = (unsigned long long *)(cand_u + ((X + 1) & ~1));                   // [X] its ytab entry for this row group
     const int YS0 = m.ys0, YSN = m.ysn;                  // rows of this map (a slab of a sharded volume, or all of them)
-    const int n_items = __ldg(n_slices) * YSN;
-    for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(work_counter, 1);
-        item = __shfl_sync(0xffffffffu, item, 0);
+    const int RG = (YSN + RPI - 1) / RPI;                // row groups per slice
+    const int n_items = __ldg(n_slices) * RG;
+    if (threadIdx.x == 0) s_item[0] = atomicAdd(work_counter, 1);
+    __syncthreads();
+    for (int it = 0;; it ^= 1) {
+        const int item = s_item[it];
         if (item >= n_items) break;
-        const int zi = item / YSN, yl = item - zi * YSN;
+        if (threadIdx.x == 0) s_item[it ^ 1] = atomicAdd(work_counter, 1);   // visible after the barriers below
+        const int zi = item / RG, rg = item - zi * RG;
         const int z = __ldg(&slice_list[zi]);
-        const int y = YS0 + yl;
-        const int wy = y >> 5, p = y & 31;               // ytab word and bit of this row
+        const int y = YS0 + rg * RPI + r;
+        const int wy = y >> 5, p = y & 31;               // ytab word and bit of this row (a row group never straddles a word)
         const int zp = compact ? zi : z;                 // plane of ytab / col_list: compacted to the real slices when received from a peer
-        const unsigned long long *trow = ytab + ((size_t)zp * WY + wy) * X;
-        const int *cols = col_list + (size_t)zp * X;
         const int nc = __ldg(&n_cols[z]);
-        // ---- 1. forward pass over this lane's band of the real columns
+        // ---- 0. stage the candidates of this (slice, word of rows)
+        {
+            const unsigned long long *trow = ytab + ((size_t)zp * WY + wy) * X;
+            const int *cols = col_list + (size_t)zp * X;
+            for (int j = threadIdx.x; j < nc; j += blockDim.x) {
+                const int u = __ldg(&cols[j]);
+                cand_u[j] = u;
+                cand_e[j] = __ldg(&trow[u]);
+            }
+        }
+        __syncthreads();   // also: the previous item's stacks, meta words and tiles are no longer read
+        // ---- 1. forward pass over this band's real columns
         {
             const int jb = (int)((long long)nc * b / NB), je = (int)((long long)nc * (b + 1) / NB);
             int q = -1, ts = 0, tt = 0, th = 0;
             const uint32_t lomask = 0xffffffffu >> (31 - p);
-            for (int j0 = jb; j0 < je; j0 += 4) {
-                // the ytab / column loads and the y-distance are independent of the scan state: batch 4 for ILP
-                int uu[4], gg[4], cc[4];
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int j = min(j0 + k, je - 1);
-                    int u = __ldg(&cols[j]);
-                    unsigned long long e = __ldg(&trow[u]);
-                    uint32_t w = (uint32_t)e;
-                    int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
-                    uint32_t mlo = w & lomask, mhi = w >> p;
-                    int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
-                    int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
-                    int g1, cy;
-                    if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
-                    else { g1 = y - lo; cy = lo; }                                          // a real column always has lo or hi
-                    uu[k] = u; gg[k] = g1 * g1; cc[k] = cy;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (j0 + k < je) band_push<1>(S, b, uu[k], gg[k], cc[k] << 20, X, q, ts, tt, th);
+            for (int j = jb; j < je; j++) {
+                const int u = cand_u[j];
+                const unsigned long long e = cand_e[j];
+                const uint32_t w = (uint32_t)e;
+                const int lo_prev = (int)((e >> 32) & 0xffff), hi_next = (int)(e >> 48);
+                const uint32_t mlo = w & lomask, mhi = w >> p;
+                const int lo = mlo ? (wy * 32 + 31 - __clz(mlo)) : (lo_prev == 0xffff ? -1 : lo_prev);
+                const int hi = mhi ? (y + __ffs(mhi) - 1) : (hi_next == 0xffff ? -1 : hi_next);
+                int g1, cy;
+                if (hi >= 0 && (lo < 0 || hi - y <= y - lo)) { g1 = hi - y; cy = hi; }   // ties -> larger y
+                else { g1 = y - lo; cy = lo; }                                          // a real column always has lo or hi
+                band_push<RPI>(S, b, u, g1 * g1, cy << 20, X, q, ts, tt, th);
             }
-            S.meta[b] = bd_meta_pack(0, q + 1, 0);
+            S.M(b) = bd_meta_pack(0, q + 1, 0);
         }
-        // ---- 2. pairwise merges: (0 <- 1), (2 <- 3), ... then (0..1 <- 2..3), ... until the row's envelope is described
-#pragma unroll
-        for (int stride = 1; stride < NB; stride <<= 1) {
-            __syncwarp();
-            if ((b & (2 * stride - 1)) == 0) band_merge<1>(S, b, stride, NB, X);
-        }
+        // ---- 2. pairwise merges: (0 <- 1), (2 <- 3), ... then (0..1 <- 2..3), ... until the row's envelope is described.
+        // The two bands of the first round live in one warp.
         __syncwarp();
-        // ---- 3. backward pass (local_edt_core.h:116-134) over this lane's x range into the row buffers
+        if ((b & 1) == 0 && b + 1 < NB) band_merge<RPI>(S, b, 1, NB, X);
+        for (int stride = 2; stride < NB; stride <<= 1) {
+            __syncthreads();
+            if ((b & (2 * stride - 1)) == 0 && b + stride < NB) band_merge<RPI>(S, b, stride, NB, X);
+        }
+        __syncthreads();
+        // ---- 3. backward pass (local_edt_core.h:116-134) over this band's x range, emitted through a RPI x TW tile
         {
             const int x_lo = b * BW, x_hi = min(X, x_lo + BW) - 1;
-            if (x_lo <= x_hi) {
-                EnvCursor<1> cur{};
-                cur.seek(S, NB, x_hi);
-                for (int u = x_hi; u >= x_lo; u--) {
+            const bool act = x_lo <= x_hi;
+            EnvCursor<RPI> cur{};
+            if (act) cur.seek(S, NB, x_hi);
+            // flush geometry: thread r stores column (r % TW) of rows r / TW, r / TW + RPI / TW, ...
+            const int col = r % TW, r0 = r / TW;
+            const bool rows_full = rg * RPI + RPI <= YSN;
+            const size_t row0 = ((size_t)z * YSN + rg * RPI + r0) * X + col;
+            for (int u = x_lo + BW - 1; u >= x_lo; u--) {
+                if (act && u <= x_hi) {
                     const int d = u - cur.es;
-                    row_g[u + b] = d * d + cur.eh;
-                    row_c[u + b] = cur.es | ((cur.eb >> 20) << 16);
+                    tile_g[r * (TW + 1) + (u & (TW - 1))] = d * d + cur.eh;
+                    tile_c[r * (TW + 1) + (u & (TW - 1))] = cur.es | ((cur.eb >> 20) << 16);
                     if (u == cur.et && u > 0) cur.prev(S);
+                }
+                if ((u & (TW - 1)) == 0) {
+                    __syncwarp();
+                    if (act && u + col < X) {
+                        int32_t *pg = g2 + row0 + u, *pc = cxy + row0 + u;
+                        const int *tg = tile_g + r0 * (TW + 1) + col, *tc = tile_c + r0 * (TW + 1) + col;
+#pragma unroll
+                        for (int k = 0; k < TW; k++) {        // RPI / (RPI / TW) = TW rows per thread
+                            if (rows_full || rg * RPI + r0 + k * (RPI / TW) < YSN) {
+                                pg[(size_t)k * (RPI / TW) * X] = tg[k * (RPI / TW) * (TW + 1)];
+                                pc[(size_t)k * (RPI / TW) * X] = tc[k * (RPI / TW) * (TW + 1)];
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
-        __syncwarp();
-        {
-            int32_t *pg = g2 + ((size_t)z * YSN + yl) * X, *pc = cxy + ((size_t)z * YSN + yl) * X;
-            for (int xx = lane; xx < X; xx += 32) {
-                const int i = xx + xx / BW;
-                pg[xx] = row_g[i];
-                pc[xx] = row_c[i];
-            }
-        }
-        __syncwarp();   // the stacks and row buffers are free for the next item
     }
 }
 
@@ -573,30 +591,36 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             int k = __ldg(&slice_list[j]);
             envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
         }
-        // backward (local_edt_core.h:169-192), one envelope segment (one owner slice) at a time: inside a segment the coc word
-        // and (s, h) are constant, so a z step is d*d + h, two streaming stores and one index bump (the first version tested
-        // `u == top.t` and bumped two 64-bit pointers every step: 23 instructions per step against ~9 here).
+        // backward (local_edt_core.h:169-192).  All lanes of the warp walk the same z (the stores stay full 128-byte lines); the
+        // walk is cut at the next z where ANY lane's envelope changes owner (warp max of the entries' starts), so that between
+        // two such events a z step is d*d + h, two streaming stores and one index bump (the first version tested `u == top.t`
+        // and bumped two 64-bit pointers every step: 23 instructions per step).
         // (_dist_id_pair is NOT written here: the reference leaves the pair of UNKNOWN voxels stale and the wavefronts relax
         // against those stale words, so only k_mark_blocks writes it, for known voxels — unify_helper.cuh:217-218.)
         size_t o = base + (size_t)(Z - 1) * slice;
         int u = Z - 1;
+        int c = __ldg(&cxy[base + (size_t)top.s * slice]);
+        int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
         for (;;) {
-            const int end = top.t, s_ = top.s, h_ = top.h;      // this entry owns z in [end, u]; the bottom entry starts at 0
+            const int nxt = __reduce_max_sync(0xffffffffu, top.t);      // every lane's entry starts at or below u
+            const int s_ = top.s, h_ = top.h;
             if (valid) {
-                const int c = __ldg(&cxy[base + (size_t)s_ * slice]);
-                const int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (s_ << 22);
 #pragma unroll 4
-                for (int v = u; v >= end; v--) {
+                for (int v = u; v >= nxt; v--) {
                     const int d = v - s_;
                     __stcs(m.aux + o, d * d + h_);
                     __stcs(m.coc_aux + o, coc_word);
                     o -= slice;
                 }
             }
-            u = end - 1;
+            u = nxt - 1;
             if (u < 0) break;
-            q--;
-            top = st.get(q);
+            if (top.t == nxt) {                                          // this lane's owner changes below nxt
+                q--;
+                top = st.get(q);
+                c = __ldg(&cxy[base + (size_t)top.s * slice]);
+                coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+            }
         }
     }
 }
@@ -639,16 +663,20 @@ int gie_edt_prepare(gie_locmap *lm)
         else if (wpc == 16) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
         else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
     }
-    // x sweep: one warp per row of an obstacle-bearing slice; persistent CTAs of XS_WARPS warps, as many as fit
+    // x sweep: one CTA per (slice, 16 rows) item; bands of ~16 columns, two bands per warp; persistent CTAs, as many as fit
     {
         XsLaunch &x = lm->xs;
-        x.NB = 32; x.CAP = (m.X + 31) / 32; x.BW = x.CAP; x.threads = XS_WARPS * 32;
-        x.smem = (size_t)XS_WARPS * (2 * 32 * x.CAP + 32 + 2 * (m.X + 32)) * 4;
+        const int nwarps = std::min(16, (m.X + 31) / 32);
+        x.rpi = XS_RPI; x.threads = nwarps * 32;
+        x.NB = nwarps * (32 / XS_RPI);
+        x.CAP = (m.X + x.NB - 1) / x.NB;
+        x.BW = ((m.X + x.NB - 1) / x.NB + XS_TW - 1) / XS_TW * XS_TW;
+        x.smem = (size_t)(2 * x.NB * x.CAP * XS_RPI + x.NB * XS_RPI + x.NB * 2 * XS_RPI * (XS_TW + 1) + ((m.X + 1) & ~1) + 2 * m.X) * 4;
         GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_xsweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x.smem));
         int xs_per_sm = 1;
         GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&xs_per_sm, k_edt_xsweep, x.threads, x.smem));
         if (xs_per_sm < 1) { gie_set_error("x sweep does not fit on an SM"); return GIE_ERR_CUDA; }
-        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, (m.Z * m.ysn + XS_WARPS - 1) / XS_WARPS);
+        lm->xs_ctas = std::min(lm->num_sms * xs_per_sm, m.Z * ((m.ysn + XS_RPI - 1) / XS_RPI));
     }
     // z sweep, dense regime: one band per warp; only when the stacks of a whole z column fit shared memory (Z <= ~880)
     {
@@ -677,8 +705,9 @@ int gie_edt_prepare(gie_locmap *lm)
 static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, int *n_slices)
 {
     const XsLaunch &x = lm->xs;
+    const BandCfg cfg{ x.NB, x.CAP, x.BW };
     k_edt_xsweep<<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices, lm->g2, lm->cxy,
-                                                                x.CAP, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
+                                                                cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
 }
 
 // dense regime first (returns at once when few slices hold obstacles), then the write-ordered serial sweep (returns at once in
