@@ -58,12 +58,14 @@ __global__ void k_pc_register(LocDev m, HashDev h, const float *__restrict__ pts
 // One thread per ray, as in the reference, leaves a B200 with ~14 warps per SM, each a chain of a few hundred dependent
 // steps (DDA step -> load of the voxel's type, which decides whether the ray stops -> decrement): 170 us at 6 active warps
 // per SM.  The walk itself is pure arithmetic, so it is split off:
-//   k_pc_walk  : thread = ray.  Runs the DDA — the same float operations in the same order as ray_cast.h:104-143, so every
-//                visited voxel is the reference's — checkpoints its state every RAY_SEG steps, and loads the voxel types of a
-//                segment without looking at them until the segment is walked (the loads complete under the arithmetic);
-//                the first OCCUPIED voxel is where the ray stops (clearRayLoc returns false).
-//   k_pc_apply : thread = (ray, segment).  Replays a segment from its checkpoint and decrements every in-volume voxel before the
-//                stop: ~20x the threads, every atomic independent of the others; the visited set and the counts are unchanged.
+//   k_pc_walk  : thread = ray.  Runs the DDA without touching memory — the same float operations in the same order as
+//                ray_cast.h:104-143, so every visited voxel is the reference's — and checkpoints its state every RAY_SEG steps.
+//   k_pc_scan  : thread = (ray, segment).  Replays the segment from its checkpoint, loads the types of its voxels (RAY_SEG
+//                independent loads) and records the first OCCUPIED one: the ray stops there (clearRayLoc returns false).
+//   k_pc_apply : thread = (ray, segment).  Replays again and decrements every in-volume voxel before the stop.
+// ~20x the threads, every load and atomic independent of the others; the visited set and the counts are unchanged.
+// (Folding the scan into the walk — the walk thread loads the types of a segment and looks at them one segment later — measured
+// slower: 0.23 ms for the stage against 0.13, the loads lengthen the one dependent chain that bounds the kernel.)
 // Every ray starts at the sensor, so the voxels around the origin are decremented by all rays: the CTAs of the first segment
 // accumulate the decrements that fall into a WIN^3 window around the origin voxel in shared memory and flush the window once
 // (sums commute, the result is identical).
@@ -106,7 +108,7 @@ __device__ __forceinline__ void ray_step(const RaySetup &r, int3 &cur, float &tm
 struct RayCk { float tmx, tmy, tmz; int x, y, z; };   // state before step s * RAY_SEG
 
 __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const float *__restrict__ pts, int n, float max_length, int max_segs,
-                                                 RayCk *__restrict__ ck, int *__restrict__ stop)
+                                                 RayCk *__restrict__ ck, int *__restrict__ nsteps, int *__restrict__ stop)
 {
     __shared__ int origin_dec;
     if (threadIdx.x == 0) origin_dec = 0;
@@ -116,40 +118,23 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
     if (i < n) {
         ray_setup(m, pts, i, r);
         // first `opr` on the origin voxel (ray_cast.h:70-72; clearRayLoc pntcld_raycast.cu:9-18): one decrement per ray
-        const int3 loc0 = r.p0i - m.pvt;
-        if (gie_inside_loc(m, loc0) && m.inst_type[gie_lidx(m, loc0)] != GIE_VOX_OCCUPIED) atomicAdd(&origin_dec, 1);
-        int steps = 0, last = 0;
+        const int3 loc = r.p0i - m.pvt;
+        if (gie_inside_loc(m, loc) && m.inst_type[gie_lidx(m, loc)] != GIE_VOX_OCCUPIED) atomicAdd(&origin_dec, 1);
+        int steps = 0;
         if (!eq3(r.p0i, r.p1i)) {
             int3 cur = r.p0i;
             float tmx = r.tmx, tmy = r.tmy, tmz = r.tmz;
             const int cap = max_segs * RAY_SEG;
-            bool fin = false;
-            while (!fin) {
-                // one segment: checkpoint, RAY_SEG steps whose voxel types are loaded but not looked at until the segment is
-                // walked (the loads complete under the arithmetic of the following steps), then the first OCCUPIED voxel, if any
-                ck[(size_t)(steps / RAY_SEG) * n + i] = RayCk{ tmx, tmy, tmz, cur.x, cur.y, cur.z };
-                const int first = steps;
-                int8_t t[RAY_SEG];
-#pragma unroll
-                for (int j = 0; j < RAY_SEG; j++) {
-                    t[j] = GIE_VOX_UNKNOWN;
-                    if (!fin) {
-                        ray_step(r, cur, tmx, tmy, tmz);
-                        steps++;
-                        const int3 loc = cur - m.pvt;
-                        if (gie_inside_loc(m, loc)) t[j] = m.inst_type[gie_lidx(m, loc)];
-                        const float d = fminf(fminf(tmx, tmy), tmz);
-                        fin = eq3(cur, r.p1i) || d > max_length || d > r.len || steps >= cap;
-                    }
-                }
-                int hit = RAY_SEG;
-#pragma unroll
-                for (int j = RAY_SEG - 1; j >= 0; j--) if (t[j] == GIE_VOX_OCCUPIED) hit = j;
-                if (first + hit < steps) { last = first + hit; fin = true; }   // the ray stops there (clearRayLoc returns false)
-                else last = steps;
+            for (;;) {
+                if ((steps & (RAY_SEG - 1)) == 0) ck[(size_t)(steps / RAY_SEG) * n + i] = RayCk{ tmx, tmy, tmz, cur.x, cur.y, cur.z };
+                ray_step(r, cur, tmx, tmy, tmz);
+                steps++;
+                const float d = fminf(fminf(tmx, tmy), tmz);
+                if (eq3(cur, r.p1i) || d > max_length || d > r.len || steps >= cap) break;
             }
         }
-        stop[i] = last;   // steps [0, last) are decremented by k_pc_apply
+        nsteps[i] = steps;
+        stop[i] = steps;   // no OCCUPIED voxel met yet: the whole walk counts
     }
     __syncthreads();
     if (threadIdx.x == 0 && origin_dec) {
@@ -161,6 +146,35 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
 }
 
 // thread = (ray, segment); CTAs are segment-major so that all threads of a CTA work on the same segment index
+__global__ void __launch_bounds__(128) k_pc_scan(LocDev m, const float *__restrict__ pts, int n, int max_segs, const RayCk *__restrict__ ck,
+                                                 const int *__restrict__ nsteps, int *__restrict__ stop)
+{
+    const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int total = __ldg(&nsteps[i]), first = seg * RAY_SEG;
+    if (first >= total) return;
+    RaySetup r;
+    ray_setup(m, pts, i, r);
+    const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
+    int3 cur = make_int3(c.x, c.y, c.z);
+    float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
+    const int cnt = min(RAY_SEG, total - first);
+    int8_t t[RAY_SEG];
+#pragma unroll
+    for (int j = 0; j < RAY_SEG; j++) {
+        t[j] = GIE_VOX_UNKNOWN;
+        if (j < cnt) {
+            ray_step(r, cur, tmx, tmy, tmz);
+            const int3 loc = cur - m.pvt;
+            if (gie_inside_loc(m, loc)) t[j] = m.inst_type[gie_lidx(m, loc)];
+        }
+    }
+    int hit = RAY_SEG;
+#pragma unroll
+    for (int j = RAY_SEG - 1; j >= 0; j--) if (t[j] == GIE_VOX_OCCUPIED) hit = j;
+    if (hit < cnt) atomicMin(&stop[i], first + hit);
+}
+
 __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, const float *__restrict__ pts, int n, int max_segs,
                                                   const RayCk *__restrict__ ck, const int *__restrict__ stop)
 {
@@ -379,11 +393,13 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
             lm->ray_scratch_bytes = need;
         }
         RayCk *ck = (RayCk *)lm->ray_scratch;
-        int *stop = (int *)((char *)lm->ray_scratch + (((size_t)n * max_segs * sizeof(RayCk) + 127) & ~(size_t)127));
+        int *nsteps = (int *)((char *)lm->ray_scratch + (((size_t)n * max_segs * sizeof(RayCk) + 127) & ~(size_t)127));
+        int *stop = nsteps + n;
         const dim3 grid2((n + 127) / 128, max_segs);
-        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, stop);
+        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, nsteps, stop);
+        k_pc_scan<<<grid2, 128, 0, lm->stream>>>(lm->d, pts_dev, n, max_segs, ck, nsteps, stop);
         k_pc_apply<<<grid2, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_segs, ck, stop);
-        lm->launches += 3;
+        lm->launches += 4;
     }
     if (fmp) {
         int r = 0;
