@@ -226,6 +226,8 @@ class ShardedMapper:
 
     def close(self):
         if self.owner is not None:
-            self.owner.close()
+            self.owner.close()          # also unmaps the peers' slabs (CUDA IPC) ...
+        if self.world > 1:
+            self.dist.barrier()         # ... before their owners free them
         for s in getattr(self, "slabs", []) + ([self.slab] if hasattr(self, "slab") else []):
             s.close()
