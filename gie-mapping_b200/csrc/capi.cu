@@ -336,12 +336,11 @@ int gie_hashmap_create(gie_hashmap **out, gie_locmap *lm, int bucket_max, int bl
     GIE_CUDA_CHECK(cudaMalloc(&h.btab, hm->tab_entries * 4));
     GIE_CUDA_CHECK(cudaMalloc(&h.touched, hm->tab_entries));
     GIE_CUDA_CHECK(cudaMemsetAsync(h.touched, 0, hm->tab_entries, s));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->merge_list, hm->tab_entries * sizeof(int)));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->merge_count, sizeof(int)));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->prev_list, hm->tab_entries * sizeof(int)));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->prev_count, sizeof(int)));
-    GIE_CUDA_CHECK(cudaMemsetAsync(hm->merge_count, 0, sizeof(int), s));
-    GIE_CUDA_CHECK(cudaMemsetAsync(hm->prev_count, 0, sizeof(int), s));
+    for (auto &bl : hm->blists) {
+        GIE_CUDA_CHECK(cudaMalloc(&bl.list, hm->tab_entries * sizeof(int)));
+        GIE_CUDA_CHECK(cudaMalloc(&bl.count, sizeof(int)));
+        GIE_CUDA_CHECK(cudaMemsetAsync(bl.count, 0, sizeof(int), s));
+    }
     GIE_CUDA_CHECK(cudaMalloc(&h.dirty, (size_t)block_max));
     GIE_CUDA_CHECK(cudaMemsetAsync(h.dirty, 0, (size_t)block_max, s));
     GIE_CUDA_CHECK(cudaMalloc(&hm->changed_list, (size_t)block_max * sizeof(int)));
@@ -365,7 +364,7 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     HashDev &h = hm->d;
     cudaFree(h.keys); cudaFree(h.vals); cudaFree(h.block_count); cudaFree(h.status); cudaFree(h.block_keys);
     cudaFree(h.occ_val); cudaFree(h.vox_type); cudaFree(h.update_ct); cudaFree(h.coc_glb); cudaFree(h.dist_sq);
-    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched); cudaFree(hm->merge_list); cudaFree(hm->merge_count); cudaFree(hm->prev_list); cudaFree(hm->prev_count); cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
+    cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched); for (auto &bl : hm->blists) { cudaFree(bl.list); cudaFree(bl.count); } cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
     cudaFree(hm->cseed_key); cudaFree(hm->counters); cudaFree(hm->barrier); cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
     cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list); cudaFree(hm->blk_count);

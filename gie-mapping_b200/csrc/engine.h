@@ -45,6 +45,7 @@ struct gie_locmap {
     bool ev_valid[GIE_ST_COUNT]{};
     long long launches = 0;
     bool glb_type_foreign = false;        // glb_type was overwritten from outside (test hook): the next merge clears all of it
+    long long ytab_serial = -1;           // OGM merge whose block list describes the y-pass bit words that are set (-1: unknown, clear all)
     gie_hashmap *hm = nullptr;
 };
 
@@ -70,12 +71,13 @@ struct gie_hashmap {
     int32_t *decA_flags = nullptr;
     uint32_t *snap_id = nullptr;  // per-queue-slot snapshot for waves B/C
     int wave_ctas = 0;
-    int *merge_list = nullptr;    // table indices of the touched or allocated blocks that intersect the volume (per OGM merge)
-    int *merge_count = nullptr;
-    int *prev_list = nullptr;     // the other buffer of the pair: swapped with merge_list every merge (see k_clear_prev_blocks)
-    int *prev_count = nullptr;
-    bool prev_valid = false;
-    int3 prev_pvt{}, prev_tab_org{};
+    // Table indices of the touched or allocated blocks that intersect the volume, per OGM merge, with the pivots they were
+    // listed under.  Two buffers: blists[bl_cur] belongs to the latest merge, the other to the one before — whatever the
+    // previous frame wrote into glb_type (and into the y-pass bit words) lies inside THOSE blocks, so that is what gets cleared.
+    struct BlockList { int *list = nullptr; int *count = nullptr; int3 pvt{}, tab_org{}; bool valid = false; };
+    BlockList blists[2];
+    int bl_cur = 0;
+    long long merge_serial = 0;   // OGM merges done so far
     int *blk_list = nullptr;      // table indices of the allocated blocks that intersect the local volume (per merge)
     int *blk_count = nullptr;
     int merge_epoch = 0;          // merges done so far; the seed mark of m.wave_layer (memset to 0 at creation)

@@ -307,22 +307,22 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     StageTimer t(lm, GIE_ST_HASH_MERGE);
     const int entries = (int)hm->tab_entries;
     // UNKNOWN wherever no block exists: clear what the previous merge may have written (the whole array only the first time
-    // and after a test upload), then swap the lists
-    if (hm->prev_valid && !lm->glb_type_foreign) {
-        k_clear_prev_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(lm->d, hm->prev_pvt, hm->prev_tab_org, hm->d.tab_dim, hm->merge_list,
-                                                                     hm->merge_count);
+    // and after a test upload), then list the blocks of this merge into the other buffer
+    gie_hashmap::BlockList &prev = hm->blists[hm->bl_cur];
+    if (prev.valid && !lm->glb_type_foreign) {
+        k_clear_prev_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
         lm->launches++;
     } else GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));
     lm->glb_type_foreign = false;
-    std::swap(hm->merge_list, hm->prev_list);
-    std::swap(hm->merge_count, hm->prev_count);
-    hm->prev_valid = true; hm->prev_pvt = lm->d.pvt; hm->prev_tab_org = hm->d.tab_org;
-    GIE_CUDA_CHECK(cudaMemsetAsync(hm->merge_count, 0, sizeof(int), lm->stream));
-    k_list_merge_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, hm->merge_list,
-                                                                                           hm->merge_count);
+    hm->bl_cur ^= 1;
+    hm->merge_serial++;
+    gie_hashmap::BlockList &cur = hm->blists[hm->bl_cur];
+    cur.valid = true; cur.pvt = lm->d.pvt; cur.tab_org = hm->d.tab_org;
+    GIE_CUDA_CHECK(cudaMemsetAsync(cur.count, 0, sizeof(int), lm->stream));
+    k_list_merge_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, cur.list, cur.count);
     const int grid = lm->num_sms * 16;
-    if (input_pntcld) k_merge_ogm<true><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, hm->merge_list, hm->merge_count);
-    else k_merge_ogm<false><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, hm->merge_list, hm->merge_count);
+    if (input_pntcld) k_merge_ogm<true><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
+    else k_merge_ogm<false><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
     lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
