@@ -48,9 +48,9 @@ def load_pkg():
 # Algorithmic bytes of the batch DT.  Two figures are reported and labelled:
 #   * `achieved` uses the bytes the three sweeps of THIS engine have to move for the frame at hand — a function of s, the
 #     fraction of z-slices that hold an obstacle (slices without one are never written by the x sweep nor read by the z sweep):
-#       y pass : 1 R (glb_type) + 0.25 W (bit words) + 0.25 R + 0.25 W (links)
+#       y pass : 0.25 R (bit words scanned for links; the bits themselves are set from the merge's block list, a few MB)
 #       x sweep: 0.25 s R (bit words) + 8 s W (g2, cxy)
-#       z sweep: 8 s R + 8 W (aux, coc_aux)                                     => 9.75 + 16.25 s  bytes per voxel
+#       z sweep: 8 s R + 8 W (aux, coc_aux)                                     => 8.25 + 16.25 s  bytes per voxel
 #     (ncu's dram__bytes for the same launches is `traffic`; the two agree within a few percent, profiles/README.md);
 #   * `survey_41B_figure` is SURVEY §8d's packed-intermediate 41 B/voxel (P1 1R+8W, P2 8R+8W, P3 8R+8W), the traffic of a
 #     design that materialises every pass for every voxel; it exceeds what is moved here and is NOT used for `frac`.
@@ -60,7 +60,7 @@ OTHER_STAGES = ("ogm", "hash_merge", "mark_frontier", "waves", "commit")
 
 
 def batch_dt_bytes_per_voxel(s):
-    return 9.75 + 16.25 * s
+    return 8.25 + 16.25 * s
 
 
 def workload_string(cfg, frames):
@@ -351,9 +351,9 @@ def run_sharded(args, gie, world, rank, local_rank):
                 "strong_scaling": ({"speedup": single["ms_per_step"] / ms_dev, "efficiency": single["ms_per_step"] / ms_dev / world}
                                    if single and "ms_per_step" in single else None),
                 "roofline": {"bound": "hbm", "kernel": "slab sweeps = k_edt_xsweep + k_edt_zsweep on the slab of the slowest rank",
-                             "achieved": (batch_dt_bytes_per_voxel(0.0) - 1.75) * nvox / world / (sweeps_max * 1e-3) / 1e9 if sweeps_max > 0 else 0.0,
+                             "achieved": (batch_dt_bytes_per_voxel(0.0) - 0.25) * nvox / world / (sweeps_max * 1e-3) / 1e9 if sweeps_max > 0 else 0.0,
                              "peak": peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
-                             "frac": ((batch_dt_bytes_per_voxel(0.0) - 1.75) * nvox / world / (sweeps_max * 1e-3) / 1e9 / peak) if sweeps_max > 0 else 0.0,
+                             "frac": ((batch_dt_bytes_per_voxel(0.0) - 0.25) * nvox / world / (sweeps_max * 1e-3) / 1e9 / peak) if sweeps_max > 0 else 0.0,
                              "traffic": None,
                              "note": "lower bound of the bytes of one slab: 8 B/voxel of aux + coc_aux written (the slice-dependent x-sweep output and "
                                      "z-sweep input are left out); per-GPU figure"},
@@ -551,7 +551,7 @@ def main():
                 "achieved": achieved, "peak": peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic.get("batch_dt"), "traffic_source": traffic.get("_file"),
                 "algorithmic_bytes_per_voxel": bpv, "algorithmic_bytes_per_launch": bpv * nvox,
-                "bytes_formula": "9.75 + 16.25 s B/voxel, s = fraction of z-slices holding an obstacle (bytes this engine's sweeps must move)",
+                "bytes_formula": "8.25 + 16.25 s B/voxel, s = fraction of z-slices holding an obstacle (bytes this engine's sweeps must move)",
                 "obstacle_slice_fraction": slice_frac,
                 "survey_41B_figure": {"bytes_per_voxel": SURVEY_BATCH_DT_BYTES, "achieved": SURVEY_BATCH_DT_BYTES * nvox / (prof["batch_dt"] * 1e-3) / 1e9
                                       if prof["batch_dt"] > 0 else None,

@@ -165,7 +165,7 @@ __device__ __forceinline__ int floor_div(int num, int den)
 
 // Envelope stack of one lane.  Entry = (h, s | t<<10 | cy<<20).  The top lives in registers; entries [base, q] live in a
 // shared-memory ring (conflict free: bank == lane), entries below `base` in the per-warp global scratch.
-struct Top { int s, t, h, cy; };
+struct Top { int s, t, h, cy; };   // site, start, height, payload (up to 22 bits: closest-obstacle coordinates of the site)
 struct LaneStack {
     int *sh;          // smem: sh[slot*32] = h words, sb = sh + RING*32 the packed words (lane offset applied)
     int *sb;
@@ -180,8 +180,8 @@ struct LaneStack {
             base++;
         }
         int sl = (q & (RING - 1)) * 32;
-        sh[sl] = e.h;
-        sb[sl] = e.s | (e.t << 10) | (e.cy << 20);
+        sh[sl] = e.h | ((e.cy >> 12) << 21);                       // h < 2^21; the payload's upper 10 bits ride above it
+        sb[sl] = e.s | (e.t << 10) | ((e.cy & 0xfff) << 20);
     }
     __device__ __forceinline__ Top get(int q)
     {
@@ -195,9 +195,9 @@ struct LaneStack {
             base = nb;
         }
         int sl = (q & (RING - 1)) * 32;
-        int b = sb[sl];
+        const uint32_t b = (uint32_t)sb[sl], hh = (uint32_t)sh[sl];
         Top e;
-        e.h = sh[sl]; e.s = b & 0x3ff; e.t = (b >> 10) & 0x3ff; e.cy = b >> 20;
+        e.h = (int)(hh & 0x1fffff); e.s = b & 0x3ff; e.t = (b >> 10) & 0x3ff; e.cy = (int)((b >> 20) | ((hh >> 21) << 12));
         return e;
     }
 };
@@ -615,22 +615,20 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         int q = -1;
         Top top{0, 0, 0, 0};
         st.base = 0;
-        // forward (EDTphase3, local_edt_core.h:146-168) over the slices that hold obstacles; loads run ahead of the scan
-        int j = 0;
-        for (; j + 4 <= ns; j += 4) {
-            int k0 = __ldg(&slice_list[j]), k1 = __ldg(&slice_list[j + 1]), k2 = __ldg(&slice_list[j + 2]), k3 = __ldg(&slice_list[j + 3]);
-            int h0 = __ldcs(&g2[base + (size_t)k0 * slice]);
-            int h1 = __ldcs(&g2[base + (size_t)k1 * slice]);
-            int h2 = __ldcs(&g2[base + (size_t)k2 * slice]);
-            int h3 = __ldcs(&g2[base + (size_t)k3 * slice]);
-            envelope_push(k0, h0, 0, Z, q, top, st);
-            envelope_push(k1, h1, 0, Z, q, top, st);
-            envelope_push(k2, h2, 0, Z, q, top, st);
-            envelope_push(k3, h3, 0, Z, q, top, st);
-        }
-        for (; j < ns; j++) {
-            int k = __ldg(&slice_list[j]);
-            envelope_push(k, __ldcs(&g2[base + (size_t)k * slice]), 0, Z, q, top, st);
+        // forward (EDTphase3, local_edt_core.h:146-168) over the slices that hold obstacles; the loads run ahead of the scan.
+        // The closest obstacle of the slice (cocx | cocy << 16) travels with the entry (20 bits of payload), so that the backward
+        // pass never has to fetch it when the owner changes — that dependent load was its largest stall.
+        for (int j0 = 0; j0 < ns; j0 += 8) {
+            int kk[8], hh[8], cc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                kk[k] = __ldg(&slice_list[min(j0 + k, ns - 1)]);
+                hh[k] = __ldcs(&g2[base + (size_t)kk[k] * slice]);
+                cc[k] = __ldcs(&cxy[base + (size_t)kk[k] * slice]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                if (j0 + k < ns) envelope_push(kk[k], hh[k], (cc[k] & 0x3ff) | ((cc[k] >> 16) << 10), Z, q, top, st);
         }
         // backward (local_edt_core.h:169-192).  All lanes of the warp walk the same z (the stores stay full 128-byte lines); the
         // walk is cut at the next z where ANY lane's envelope changes owner (warp max of the entries' starts), so that between
@@ -640,8 +638,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         // against those stale words, so only k_mark_blocks writes it, for known voxels — unify_helper.cuh:217-218.)
         size_t o = base + (size_t)(Z - 1) * slice;
         int u = Z - 1;
-        int c = __ldg(&cxy[base + (size_t)top.s * slice]);
-        int coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+        int coc_word = (top.cy & 0x3ff) | ((top.cy >> 10) << 11) | (top.s << 22);
         for (;;) {
             const int nxt = __reduce_max_sync(0xffffffffu, top.t);      // every lane's entry starts at or below u
             const int s_ = top.s, h_ = top.h;
@@ -659,8 +656,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             if (top.t == nxt) {                                          // this lane's owner changes below nxt
                 q--;
                 top = st.get(q);
-                c = __ldg(&cxy[base + (size_t)top.s * slice]);
-                coc_word = (c & 0xffff) | ((c >> 16) << 11) | (top.s << 22);
+                coc_word = (top.cy & 0x3ff) | ((top.cy >> 10) << 11) | (top.s << 22);
             }
         }
     }
