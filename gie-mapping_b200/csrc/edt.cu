@@ -576,15 +576,15 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
     }
 }
 
-template <int WARPS_PER_CTA>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 32 / WARPS_PER_CTA)
+constexpr int ZS_WARPS = 8;
+__global__ void __launch_bounds__(ZS_WARPS * 32, 32 / ZS_WARPS)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
              int XG, int banded_dense)
 {
-    extern __shared__ int zs_ring[];   // [WARPS_PER_CTA][2 * RING * 32]
+    __shared__ int zs_ring[ZS_WARPS * 2 * RING * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int gwarp = blockIdx.x * WARPS_PER_CTA + wid;
+    const int gwarp = blockIdx.x * ZS_WARPS + wid;
     LaneStack st;
     st.sh = zs_ring + wid * 2 * RING * 32 + lane; st.sb = st.sh + RING * 32;
     st.g = scratch + (size_t)gwarp * L * 32 + lane;
@@ -700,24 +700,12 @@ int gie_edt_prepare(gie_locmap *lm)
     GIE_CUDA_CHECK(cudaMalloc(&lm->col_list, (size_t)m.Z * m.X * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->edt_meta, (size_t)(2 * m.Z + 8) * 4));   // n_cols[Z], slice_list[Z], n_slices
     int L = m.X > m.Z ? m.X : m.Z;
-    // serial z sweep: WARPS_PER_CTA adjacent x groups of one row per CTA (the width of the contiguous run a lockstep z step
-    // writes: 128 B x warps per array); 32 warps per SM in all shapes.  GIE_ZS_WPC overrides (measurement switch).
-    int wpc = 8;
-    if (getenv("GIE_ZS_WPC")) { int v = atoi(getenv("GIE_ZS_WPC")); if (v == 8 || v == 16 || v == 32) wpc = v; }
-    while (wpc > 8 && wpc * 32 > 2 * m.X) wpc >>= 1;   // no wider than the row
-    lm->zs_wpc = wpc;
-    const int WARPS_PER_CTA = wpc;
+    // serial z sweep: persistent CTAs of ZS_WARPS warps, 32 warps per SM; every warp pulls (row, 32 x) items
     int n_items = m.ysn * ((m.X + 31) / 32);
-    int ctas = lm->num_sms * (32 / wpc);
-    int need = (n_items + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    int ctas = lm->num_sms * (32 / ZS_WARPS);
+    int need = (n_items + ZS_WARPS - 1) / ZS_WARPS;
     if (need < ctas) ctas = need;   // small volumes: no idle persistent CTAs
     lm->edt_ctas = ctas;
-    {
-        const int ring_bytes = wpc * 2 * RING * 32 * (int)sizeof(int);
-        if (wpc == 32) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
-        else if (wpc == 16) GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
-        else GIE_CUDA_CHECK(cudaFuncSetAttribute(k_edt_zsweep<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ring_bytes));
-    }
     // x sweep: one CTA per (slice, 16 rows) item; bands of ~16 columns, two bands per warp; persistent CTAs, as many as fit
     {
         XsLaunch &x = lm->xs;
@@ -751,7 +739,7 @@ int gie_edt_prepare(gie_locmap *lm)
             lm->zs_ctas = std::min(lm->num_sms * std::max(per_sm, 1), m.ysn * ((m.X + 31) / 32));
         }
     }
-    lm->stack_scratch_entries = (size_t)ctas * WARPS_PER_CTA * L * 32;
+    lm->stack_scratch_entries = (size_t)ctas * ZS_WARPS * L * 32;
     GIE_CUDA_CHECK(cudaMalloc(&lm->stack_scratch, lm->stack_scratch_entries * 8));
     GIE_CUDA_CHECK(cudaMalloc(&lm->work_counters, 4 * sizeof(int)));
     return GIE_OK;
@@ -771,8 +759,6 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
 {
     const int XG = (m.X + 31) / 32;
     const int L = m.X > m.Z ? m.X : m.Z;
-    const int wpc = lm->zs_wpc;
-    const size_t ring_bytes = (size_t)wpc * 2 * RING * 32 * sizeof(int);
     const int n_items = m.ysn * XG;
     if (lm->zs_banded) {
         const BandCfg cfg{ lm->zs.NB, lm->zs.CAP, lm->zs.BW };
@@ -780,10 +766,8 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
                                                                                      lm->work_counters + 2);
         lm->launches++;
     }
-#define GIE_ZS_LAUNCH(W) k_edt_zsweep<W><<<lm->edt_ctas, W * 32, ring_bytes, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, \
-        (uint2 *)lm->stack_scratch, L, lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0)
-    if (wpc == 32) GIE_ZS_LAUNCH(32); else if (wpc == 16) GIE_ZS_LAUNCH(16); else GIE_ZS_LAUNCH(8);
-#undef GIE_ZS_LAUNCH
+    k_edt_zsweep<<<lm->edt_ctas, ZS_WARPS * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
+                                                                 lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0);
     lm->launches++;
 }
 

@@ -30,7 +30,6 @@ struct gie_locmap {
     int n_ipc_opened = 0;
     XsLaunch zs;                          // banded z sweep (dense regime)
     bool zs_banded = false;
-    int zs_wpc = 8;                       // warps per CTA of the serial z sweep
     int zs_ctas = 0;
     int *work_counters = nullptr;         // device: [4]
     // ray-cast scratch: per-ray checkpoints, step counts and stop indices (ogm.cu)
