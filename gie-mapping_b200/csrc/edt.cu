@@ -28,7 +28,6 @@
 namespace {
 
 constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
-constexpr int RING = 16;      // stack entries per lane kept in shared memory
 
 // y pass, step 1: OCCUPIED bits of 32 consecutive y per (z, wy, x) -> low word of ytab.  One thread per VEC adjacent words
 // (x fastest): 32 coalesced loads of VEC bytes in flight per thread, 128 bytes per warp instruction at VEC = 4.
@@ -163,11 +162,13 @@ __device__ __forceinline__ int floor_div(int num, int den)
     return q;
 }
 
-// Envelope stack of one lane.  Entry = (h, s | t<<10 | cy<<20).  The top lives in registers; entries [base, q] live in a
+// Envelope stack of one lane.  Entry = (cw, h | t<<21) with cw = cocx | cocy<<11 | s<<22, the closest-obstacle word the
+// backward pass stores as it is (h < 2^21, t < 2^10).  The top lives in registers; entries [base, q] live in a
 // shared-memory ring (conflict free: bank == lane), entries below `base` in the per-warp global scratch.
-struct Top { int s, t, h, cy; };   // site, start, height, payload (up to 22 bits: closest-obstacle coordinates of the site)
+struct Top { int s, t, h, cw; };   // site, start, height, closest-obstacle word of the site (carries s in its top 10 bits)
+template <int RING>
 struct LaneStack {
-    int *sh;          // smem: sh[slot*32] = h words, sb = sh + RING*32 the packed words (lane offset applied)
+    int *sh;          // smem: sh[slot*32] = cw words, sb = sh + RING*32 the (h, t) words (lane offset applied)
     int *sb;
     uint2 *g;         // global scratch, lane offset applied, stride 32
     int base;
@@ -175,13 +176,13 @@ struct LaneStack {
     {
         if (q < base) base = q;
         else if (q - base >= RING) {
-            int sl = (base & (RING - 1)) * 32;
+            int sl = (base % RING) * 32;
             g[base * 32] = make_uint2((uint32_t)sh[sl], (uint32_t)sb[sl]);
             base++;
         }
-        int sl = (q & (RING - 1)) * 32;
-        sh[sl] = e.h | ((e.cy >> 12) << 21);                       // h < 2^21; the payload's upper 10 bits ride above it
-        sb[sl] = e.s | (e.t << 10) | ((e.cy & 0xfff) << 20);
+        int sl = (q % RING) * 32;
+        sh[sl] = e.cw;
+        sb[sl] = e.h | (e.t << 21);
     }
     __device__ __forceinline__ Top get(int q)
     {
@@ -189,21 +190,22 @@ struct LaneStack {
             int nb = max(0, q - RING / 2 + 1);
             for (int i = nb; i <= q; i++) {
                 uint2 v = g[i * 32];
-                int sl = (i & (RING - 1)) * 32;
+                int sl = (i % RING) * 32;
                 sh[sl] = (int)v.x; sb[sl] = (int)v.y;
             }
             base = nb;
         }
-        int sl = (q & (RING - 1)) * 32;
-        const uint32_t b = (uint32_t)sb[sl], hh = (uint32_t)sh[sl];
+        int sl = (q % RING) * 32;
+        const uint32_t b = (uint32_t)sb[sl];
         Top e;
-        e.h = (int)(hh & 0x1fffff); e.s = b & 0x3ff; e.t = (b >> 10) & 0x3ff; e.cy = (int)((b >> 20) | ((hh >> 21) << 12));
+        e.cw = sh[sl]; e.s = (int)((uint32_t)e.cw >> 22); e.h = (int)(b & 0x1fffff); e.t = (int)(b >> 21);
         return e;
     }
 };
 
 // one step of the lower-envelope construction (EDTphase2/3 forward loops, local_edt_core.h:93-115 / :146-168)
-__device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, int &q, Top &top, LaneStack &st)
+template <int RING>
+__device__ __forceinline__ void envelope_push(int u, int h_u, int cw_u, int L, int &q, Top &top, LaneStack<RING> &st)
 {
     while (q >= 0) {
         int a = top.t - top.s, b = top.t - u;
@@ -214,7 +216,7 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
     }
     if (q < 0) {
         q = 0;
-        top.s = u; top.t = 0; top.h = h_u; top.cy = cy_u;
+        top.s = u; top.t = 0; top.h = h_u; top.cw = cw_u;
         st.put(0, top);
     } else {
         int num = u * u - top.s * top.s + h_u - top.h;
@@ -222,7 +224,7 @@ __device__ __forceinline__ void envelope_push(int u, int h_u, int cy_u, int L, i
         int w = 1 + floor_div(num, den);
         if (w < L) {
             q++;
-            top.s = u; top.t = w; top.h = h_u; top.cy = cy_u;
+            top.s = u; top.t = w; top.h = h_u; top.cw = cw_u;
             st.put(q, top);
         }
     }
@@ -577,16 +579,17 @@ k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__r
 }
 
 constexpr int ZS_WARPS = 8;
+constexpr int ZS_RING = 16;    // envelope entries per lane kept in shared memory (deeper ones spill to an L2-resident scratch)
 __global__ void __launch_bounds__(ZS_WARPS * 32, 32 / ZS_WARPS)
 k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
              int XG, int banded_dense)
 {
-    __shared__ int zs_ring[ZS_WARPS * 2 * RING * 32];
+    __shared__ int zs_ring[ZS_WARPS * 2 * ZS_RING * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * ZS_WARPS + wid;
-    LaneStack st;
-    st.sh = zs_ring + wid * 2 * RING * 32 + lane; st.sb = st.sh + RING * 32;
+    LaneStack<ZS_RING> st;
+    st.sh = zs_ring + wid * 2 * ZS_RING * 32 + lane; st.sb = st.sh + ZS_RING * 32;
     st.g = scratch + (size_t)gwarp * L * 32 + lane;
     const int X = m.X, Z = m.Z, S = m.max_width;
     const size_t slice = (size_t)X * m.ysn;            // the arrays are [Z][ysn][X]: a slab of the rows, or all of them
@@ -628,7 +631,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
             }
 #pragma unroll
             for (int k = 0; k < 8; k++)
-                if (j0 + k < ns) envelope_push(kk[k], hh[k], (cc[k] & 0x3ff) | ((cc[k] >> 16) << 10), Z, q, top, st);
+                if (j0 + k < ns) envelope_push(kk[k], hh[k], (cc[k] & 0x7ff) | ((cc[k] >> 16) << 11) | (kk[k] << 22), Z, q, top, st);
         }
         // backward (local_edt_core.h:169-192).  All lanes of the warp walk the same z (the stores stay full 128-byte lines); the
         // walk is cut at the next z where ANY lane's envelope changes owner (warp max of the entries' starts), so that between
@@ -637,27 +640,27 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
         // (_dist_id_pair is NOT written here: the reference leaves the pair of UNKNOWN voxels stale and the wavefronts relax
         // against those stale words, so only k_mark_blocks writes it, for known voxels — unify_helper.cuh:217-218.)
         size_t o = base + (size_t)(Z - 1) * slice;
-        int u = Z - 1;
-        int coc_word = (top.cy & 0x3ff) | ((top.cy >> 10) << 11) | (top.s << 22);
-        for (;;) {
-            const int nxt = __reduce_max_sync(0xffffffffu, top.t);      // every lane's entry starts at or below u
-            const int s_ = top.s, h_ = top.h;
+        // Every z step tests this lane's own breakpoint; the pop path runs for the warp whenever any lane changes owner, and the
+        // warp is re-converged after it: lanes that drift apart would store partial lines (measured: 6 ms instead of 0.28).
+        // (Cutting the walk at the warp-wide maximum of the breakpoints instead — a branch-free inner loop between cuts —
+        // executes fewer instructions but times the same on the scene and 5 % slower on dense volumes: the sweep is bound by
+        // the memory system, profiles/r02_edt_experiments.md.)
+        int32_t *pa = m.aux + o, *pc = m.coc_aux + o;
+        int s_ = top.s, h_ = top.h, cw_ = top.cw, t_ = top.t;
+        for (int v = Z - 1;; v--) {
+            const int d = v - s_;
             if (valid) {
-#pragma unroll 4
-                for (int v = u; v >= nxt; v--) {
-                    const int d = v - s_;
-                    __stcs(m.aux + o, d * d + h_);
-                    __stcs(m.coc_aux + o, coc_word);
-                    o -= slice;
-                }
+                __stcs(pa, d * d + h_);
+                __stcs(pc, cw_);
             }
-            u = nxt - 1;
-            if (u < 0) break;
-            if (top.t == nxt) {                                          // this lane's owner changes below nxt
+            if (v == t_) {                       // entry 0 starts at 0, every other entry above it: all lanes leave at v == 0
+                if (q == 0) break;
                 q--;
-                top = st.get(q);
-                coc_word = (top.cy & 0x3ff) | ((top.cy >> 10) << 11) | (top.s << 22);
+                const Top e = st.get(q);
+                s_ = e.s; h_ = e.h; cw_ = e.cw; t_ = e.t;
             }
+            __syncwarp();
+            pa -= slice; pc -= slice;
         }
     }
 }

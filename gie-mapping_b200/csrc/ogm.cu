@@ -96,19 +96,37 @@ __device__ __forceinline__ void ray_setup(const LocDev &m, const float *__restri
     if (r.sy != 0) { float b = (float)r.p0i.y * m.w + (float)r.sy * m.w * 0.5f; r.tmy = (b - r.p0.y) / dy; r.tdy = m.w / fabsf(dy); }
     if (r.sz != 0) { float b = (float)r.p0i.z * m.w + (float)r.sz * m.w * 0.5f; r.tmz = (b - r.p0.z) / dz; r.tdz = m.w / fabsf(dz); }
 }
-// one DDA step: the comparison tree of ray_cast.h:107-114, reproduced literally
-__device__ __forceinline__ void ray_step(const RaySetup &r, int3 &cur, float &tmx, float &tmy, float &tmz)
+// What a DDA step needs of the set-up: k_pc_walk stores it per ray (16 bytes), the (ray, segment) threads of k_pc_scan /
+// k_pc_apply load it instead of redoing the set-up's six IEEE divisions and the square root.
+struct RayInc { float tdx, tdy, tdz; int sx, sy, sz; };
+__device__ __forceinline__ RayInc ray_inc(const RaySetup &r) { return RayInc{ r.tdx, r.tdy, r.tdz, r.sx, r.sy, r.sz }; }
+__device__ __forceinline__ float4 ray_inc_pack(const RayInc &r)
 {
-    if (tmx < tmy) {
-        if (tmx < tmz) { cur.x += r.sx; tmx += r.tdx; } else { cur.z += r.sz; tmz += r.tdz; }
-    } else {
-        if (tmy < tmz) { cur.y += r.sy; tmy += r.tdy; } else { cur.z += r.sz; tmz += r.tdz; }
-    }
+    return make_float4(r.tdx, r.tdy, r.tdz, __int_as_float((r.sx + 1) | ((r.sy + 1) << 2) | ((r.sz + 1) << 4)));
+}
+__device__ __forceinline__ RayInc ray_inc_unpack(float4 v)
+{
+    const int b = __float_as_int(v.w);
+    return RayInc{ v.x, v.y, v.z, (b & 3) - 1, ((b >> 2) & 3) - 1, ((b >> 4) & 3) - 1 };
+}
+// one DDA step: the comparison tree of ray_cast.h:107-114 — (tmx < tmy) ? (tmx < tmz ? x : z) : (tmy < tmz ? y : z) — written
+// without branches: the smaller of (x, y) by the first comparison meets z in the second.  Same comparisons on the same
+// values, same single addition; the step is the dependent chain that bounds the walk, and the select form halves it.
+__device__ __forceinline__ void ray_step(const RayInc &r, int3 &cur, float &tmx, float &tmy, float &tmz)
+{
+    const bool xm = tmx < tmy;
+    const float a = xm ? tmx : tmy;
+    const bool zw = !(a < tmz);
+    const bool stepx = xm && !zw, stepy = !xm && !zw;
+    if (stepx) { cur.x += r.sx; tmx += r.tdx; }
+    if (stepy) { cur.y += r.sy; tmy += r.tdy; }
+    if (zw) { cur.z += r.sz; tmz += r.tdz; }
 }
 struct RayCk { float tmx, tmy, tmz; int x, y, z; };   // state before step s * RAY_SEG
 
 __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const float *__restrict__ pts, int n, float max_length, int max_segs,
-                                                 RayCk *__restrict__ ck, int *__restrict__ nsteps, int *__restrict__ stop)
+                                                 RayCk *__restrict__ ck, float4 *__restrict__ incs, int *__restrict__ nsteps,
+                                                 int *__restrict__ stop)
 {
     __shared__ int origin_dec;
     if (threadIdx.x == 0) origin_dec = 0;
@@ -121,13 +139,15 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
         const int3 loc = r.p0i - m.pvt;
         if (gie_inside_loc(m, loc) && m.inst_type[gie_lidx(m, loc)] != GIE_VOX_OCCUPIED) atomicAdd(&origin_dec, 1);
         int steps = 0;
+        const RayInc inc = ray_inc(r);
+        incs[i] = ray_inc_pack(inc);
         if (!eq3(r.p0i, r.p1i)) {
             int3 cur = r.p0i;
             float tmx = r.tmx, tmy = r.tmy, tmz = r.tmz;
             const int cap = max_segs * RAY_SEG;
             for (;;) {
                 if ((steps & (RAY_SEG - 1)) == 0) ck[(size_t)(steps / RAY_SEG) * n + i] = RayCk{ tmx, tmy, tmz, cur.x, cur.y, cur.z };
-                ray_step(r, cur, tmx, tmy, tmz);
+                ray_step(inc, cur, tmx, tmy, tmz);
                 steps++;
                 const float d = fminf(fminf(tmx, tmy), tmz);
                 if (eq3(cur, r.p1i) || d > max_length || d > r.len || steps >= cap) break;
@@ -146,15 +166,14 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
 }
 
 // thread = (ray, segment); CTAs are segment-major so that all threads of a CTA work on the same segment index
-__global__ void __launch_bounds__(128) k_pc_scan(LocDev m, const float *__restrict__ pts, int n, int max_segs, const RayCk *__restrict__ ck,
-                                                 const int *__restrict__ nsteps, int *__restrict__ stop)
+__global__ void __launch_bounds__(128) k_pc_scan(LocDev m, int n, int max_segs, const RayCk *__restrict__ ck,
+                                                 const float4 *__restrict__ incs, const int *__restrict__ nsteps, int *__restrict__ stop)
 {
     const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int total = __ldg(&nsteps[i]), first = seg * RAY_SEG;
     if (first >= total) return;
-    RaySetup r;
-    ray_setup(m, pts, i, r);
+    const RayInc r = ray_inc_unpack(__ldg(&incs[i]));
     const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
     int3 cur = make_int3(c.x, c.y, c.z);
     float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
@@ -175,8 +194,8 @@ __global__ void __launch_bounds__(128) k_pc_scan(LocDev m, const float *__restri
     if (hit < cnt) atomicMin(&stop[i], first + hit);
 }
 
-__global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, const float *__restrict__ pts, int n, int max_segs,
-                                                  const RayCk *__restrict__ ck, const int *__restrict__ stop)
+__global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, int max_segs, const RayCk *__restrict__ ck,
+                                                  const float4 *__restrict__ incs, const int *__restrict__ stop)
 {
     __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
     const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,8 +209,7 @@ __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, const flo
     const int first = seg * RAY_SEG;
     const int last = i < n ? __ldg(&stop[i]) : 0;                    // steps [0, last) are decremented
     if (i < n && first < last) {
-        RaySetup r;
-        ray_setup(m, pts, i, r);
+        const RayInc r = ray_inc_unpack(__ldg(&incs[i]));
         const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
         int3 cur = make_int3(c.x, c.y, c.z);
         float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
@@ -386,19 +404,20 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
         // a walk crosses at most (|dx| + |dy| + |dz|) <= sqrt(3) voxel borders per voxel of length: bound on the segments of a ray
         const int max_steps = (int)(0.707f * (float)lm->d.X * 1.7320508f) + 8;
         const int max_segs = (max_steps + RAY_SEG - 1) / RAY_SEG;
-        const size_t need = (size_t)n * max_segs * sizeof(RayCk) + (size_t)n * 2 * sizeof(int) + 256;
+        const size_t need = (size_t)n * max_segs * sizeof(RayCk) + (size_t)n * (2 * sizeof(int) + sizeof(float4)) + 512;
         if (lm->ray_scratch_bytes < need) {
             if (lm->ray_scratch) { GIE_CUDA_CHECK(cudaStreamSynchronize(lm->stream)); GIE_CUDA_CHECK(cudaFree(lm->ray_scratch)); lm->ray_scratch = nullptr; }
             GIE_CUDA_CHECK(cudaMalloc(&lm->ray_scratch, need));
             lm->ray_scratch_bytes = need;
         }
         RayCk *ck = (RayCk *)lm->ray_scratch;
-        int *nsteps = (int *)((char *)lm->ray_scratch + (((size_t)n * max_segs * sizeof(RayCk) + 127) & ~(size_t)127));
+        float4 *incs = (float4 *)((char *)lm->ray_scratch + (((size_t)n * max_segs * sizeof(RayCk) + 127) & ~(size_t)127));
+        int *nsteps = (int *)(incs + n);
         int *stop = nsteps + n;
         const dim3 grid2((n + 127) / 128, max_segs);
-        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, nsteps, stop);
-        k_pc_scan<<<grid2, 128, 0, lm->stream>>>(lm->d, pts_dev, n, max_segs, ck, nsteps, stop);
-        k_pc_apply<<<grid2, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_segs, ck, stop);
+        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, incs, nsteps, stop);
+        k_pc_scan<<<grid2, 128, 0, lm->stream>>>(lm->d, n, max_segs, ck, incs, nsteps, stop);
+        k_pc_apply<<<grid2, 128, 0, lm->stream>>>(lm->d, hm->d, n, max_segs, ck, incs, stop);
         lm->launches += 4;
     }
     if (fmp) {

@@ -20,6 +20,49 @@ __global__ void k_zwalk(int *a, int *b, int X, int Y, int Z, int zchunk)
         for (int u = 0; u < zchunk; u++) { __stcs(a + o, u); __stcs(b + o, u + 1); o -= slice; }
     }
 }
+// The same stores issued the way the z sweep issues them: warps pull (row, x group) items from a counter; optionally a forward
+// phase first (NS slices of two input arrays, 8 loads per dependent batch) and a shared-memory read every POPEVERY steps.
+template <int FWD, int POPEVERY>
+__global__ void __launch_bounds__(256, 4) k_zwalk_dyn(int *a, int *b, const int *g, const int *c, int X, int Y, int Z, int ns, int *counter)
+{
+    __shared__ int ring[8 * 32 * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int XG = X / 32, n_items = Y * XG;
+    const size_t slice = (size_t)X * Y;
+    int *my = ring + wid * 32 * 32 + lane;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int y = item / XG, x = (item % XG) * 32 + lane;
+        const size_t base = (size_t)y * X + x;
+        int acc = 0;
+        if (FWD) {
+            for (int j0 = 0; j0 < ns; j0 += 8) {
+                int hh[8], cc[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int kk = min(j0 + k, ns - 1) * (Z / ns);
+                    hh[k] = __ldcs(&g[base + (size_t)kk * slice]);
+                    cc[k] = __ldcs(&c[base + (size_t)kk * slice]);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) { acc += hh[k] ^ cc[k]; my[((j0 + k) & 31) * 32] = acc; }
+            }
+        }
+        size_t o = base + (size_t)(Z - 1) * slice;
+        int *pa = a + o, *pb = b + o;
+        int h = acc, t = Z - 3;
+        for (int v = Z - 1; v >= 0; v--) {
+            const int d = v - 7;
+            __stcs(pa, d * d + h); __stcs(pb, h);
+            if (POPEVERY && v == t) { h = my[(v & 31) * 32]; t = v - POPEVERY - (h & 1); }
+            if (POPEVERY) __syncwarp();
+            pa -= slice; pb -= slice;
+        }
+    }
+}
 __global__ void k_linear(int *a, int *b, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) { __stcs(a + i, 1); __stcs(b + i, 2); }
@@ -47,6 +90,21 @@ int main(int argc, char **argv)
         timeit(name, [&] { k_zwalk<<<148 * 4, 256>>>(a, b, X, Y, Z, zc); });
         snprintf(name, sizeof name, "z walk, chunk %d, 148x8 CTAs x 8 warps", zc);
         timeit(name, [&] { k_zwalk<<<148 * 8, 256>>>(a, b, X, Y, Z, zc); });
+    }
+    int *g, *c, *counter;
+    cudaMalloc(&g, n * 4); cudaMalloc(&c, n * 4); cudaMalloc(&counter, 4);
+    cudaMemset(g, 0, n * 4); cudaMemset(c, 0, n * 4);
+    const int ns = 55;
+    for (int mult : { 4, 8 }) {
+        char name[96];
+        snprintf(name, sizeof name, "dynamic items, stores only, 148x%d CTAs", mult);
+        timeit(name, [&] { cudaMemsetAsync(counter, 0, 4); k_zwalk_dyn<0, 0><<<148 * mult, 256>>>(a, b, g, c, X, Y, Z, ns, counter); });
+        snprintf(name, sizeof name, "dynamic + forward loads (55 slices), 148x%d", mult);
+        timeit(name, [&] { cudaMemsetAsync(counter, 0, 4); k_zwalk_dyn<1, 0><<<148 * mult, 256>>>(a, b, g, c, X, Y, Z, ns, counter); });
+        snprintf(name, sizeof name, "dynamic + forward + pop every ~3 steps, 148x%d", mult);
+        timeit(name, [&] { cudaMemsetAsync(counter, 0, 4); k_zwalk_dyn<1, 3><<<148 * mult, 256>>>(a, b, g, c, X, Y, Z, ns, counter); });
+        snprintf(name, sizeof name, "dynamic + pop every ~3 steps (no forward), 148x%d", mult);
+        timeit(name, [&] { cudaMemsetAsync(counter, 0, 4); k_zwalk_dyn<0, 3><<<148 * mult, 256>>>(a, b, g, c, X, Y, Z, ns, counter); });
     }
     if (cudaDeviceSynchronize() != cudaSuccess) { printf("CUDA error\n"); return 1; }
     return 0;
