@@ -10,6 +10,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// first statement of every kernel launched through gie_launch (engine.h): let the next kernel of the stream be placed, then
+// wait for the previous one to complete
+#if defined(__CUDACC__)
+__device__ __forceinline__ void gie_pdl_sync()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 #define GIE_VOX_UNKNOWN 0
 #define GIE_VOX_FREE 1
 #define GIE_VOX_OCCUPIED 2

@@ -34,6 +34,7 @@ constexpr int INV_Y = 2045;   // INVALID_LOC_COC.y, local_batch.h:59
 template <int VEC>
 __global__ void __launch_bounds__(128) k_edt_ybits(LocDev m, unsigned long long *__restrict__ ytab, int WY)
 {
+    gie_pdl_sync();
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * VEC, wy = blockIdx.y, z = blockIdx.z;
     if (x >= m.X) return;
     const int ybase = wy * 32, n = min(32, m.Y - ybase);
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(128) k_edt_ybits(LocDev m, unsigned long long 
 __global__ void __launch_bounds__(256) k_edt_ybits_clear(LocDev m, unsigned long long *__restrict__ ytab, int WY, int3 pvt, int3 tab_org, int3 tab_dim,
                                                          const int *__restrict__ list, const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     const int sub = threadIdx.x >> 6, col = threadIdx.x & 63;     // 4 blocks per CTA pass
     for (int b = blockIdx.x * 4 + sub; b < n; b += gridDim.x * 4) {
@@ -75,6 +77,7 @@ __global__ void __launch_bounds__(256) k_edt_ybits_clear(LocDev m, unsigned long
 __global__ void __launch_bounds__(256) k_edt_ybits_blocks(LocDev m, unsigned long long *__restrict__ ytab, int WY, int3 tab_org, int3 tab_dim,
                                                           const int32_t *__restrict__ btab, const int *__restrict__ list, const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     const int sub = threadIdx.x >> 6, col = threadIdx.x & 63;
     for (int b = blockIdx.x * 4 + sub; b < n; b += gridDim.x * 4) {
@@ -100,6 +103,7 @@ __global__ void __launch_bounds__(256) k_edt_ybits_blocks(LocDev m, unsigned lon
 __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long *__restrict__ ytab, int WY,
                                                     int *__restrict__ col_list, int *__restrict__ n_cols)
 {
+    gie_pdl_sync();
     __shared__ int warp_cnt[32];
     const int x = threadIdx.x, z = blockIdx.x;
     const int lane = x & 31, wid = x >> 5;
@@ -140,6 +144,7 @@ __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long
 __global__ void __launch_bounds__(1024) k_edt_slices(int Z, const int *__restrict__ n_cols, int *__restrict__ slice_list,
                                                      int *__restrict__ n_slices)
 {
+    gie_pdl_sync();
     __shared__ int warp_cnt[32];
     const int z = threadIdx.x, lane = z & 31, wid = z >> 5;
     bool any = z < Z && n_cols[z] > 0;
@@ -390,6 +395,7 @@ k_edt_xsweep(LocDev m, const unsigned long long *__restrict__ ytab, int WY, cons
              const int *__restrict__ n_cols, const int *__restrict__ slice_list, const int *__restrict__ n_slices,
              int32_t *__restrict__ g2, int32_t *__restrict__ cxy, BandCfg cfg, int *__restrict__ work_counter, int compact)
 {
+    gie_pdl_sync();
     constexpr int RPI = XS_RPI, TW = XS_TW;
     extern __shared__ int xs_smem[];
     __shared__ int s_item[2];
@@ -507,6 +513,7 @@ __global__ void __launch_bounds__(512)
 k_edt_zsweep_banded(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict__ cxy, const int *__restrict__ slice_list,
                     const int *__restrict__ n_slices, BandCfg cfg, int *__restrict__ work_counter)
 {
+    gie_pdl_sync();
     extern __shared__ int zs_smem[];
     __shared__ int s_item;
     const int X = m.X, Z = m.Z;
@@ -585,6 +592,7 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
              const int *__restrict__ n_slices, uint2 *__restrict__ scratch, int L, int *__restrict__ work_counter, int n_items,
              int XG, int banded_dense)
 {
+    gie_pdl_sync();
     __shared__ int zs_ring[ZS_WARPS * 2 * ZS_RING * 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * ZS_WARPS + wid;
@@ -674,19 +682,19 @@ int launch_ybits(gie_locmap *lm, int WY)
         const gie_hashmap::BlockList &cur = hm->blists[hm->bl_cur], &prev = hm->blists[hm->bl_cur ^ 1];
         const size_t words = (size_t)m.Z * WY * m.X;
         if (lm->ytab_serial == hm->merge_serial - 1 && prev.valid)
-            k_edt_ybits_clear<<<lm->num_sms * 4, 256, 0, lm->stream>>>(m, lm->ytab, WY, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
+            gie_launch(k_edt_ybits_clear, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
         else if (lm->ytab_serial != hm->merge_serial)
             GIE_CUDA_CHECK(cudaMemsetAsync(lm->ytab, 0, words * 8, lm->stream));
         else   // a second batch EDT on the same merge: clear what this merge's own list set
-            k_edt_ybits_clear<<<lm->num_sms * 4, 256, 0, lm->stream>>>(m, lm->ytab, WY, cur.pvt, cur.tab_org, hm->d.tab_dim, cur.list, cur.count);
-        k_edt_ybits_blocks<<<lm->num_sms * 4, 256, 0, lm->stream>>>(m, lm->ytab, WY, cur.tab_org, hm->d.tab_dim, hm->d.btab, cur.list, cur.count);
+            gie_launch(k_edt_ybits_clear, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, cur.pvt, cur.tab_org, hm->d.tab_dim, cur.list, cur.count);
+        gie_launch(k_edt_ybits_blocks, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, cur.tab_org, hm->d.tab_dim, hm->d.btab, cur.list, cur.count);
         lm->ytab_serial = hm->merge_serial;
         lm->launches++;
         return GIE_OK;
     }
     lm->ytab_serial = -1;
-    if (m.X % 4 == 0) k_edt_ybits<4><<<dim3((m.X / 4 + 127) / 128, WY, m.Z), 128, 0, lm->stream>>>(m, lm->ytab, WY);
-    else k_edt_ybits<1><<<dim3((m.X + 127) / 128, WY, m.Z), 128, 0, lm->stream>>>(m, lm->ytab, WY);
+    if (m.X % 4 == 0) gie_launch(k_edt_ybits<4>, dim3((m.X / 4 + 127) / 128, WY, m.Z), dim3(128), 0, lm->stream, m, lm->ytab, WY);
+    else gie_launch(k_edt_ybits<1>, dim3((m.X + 127) / 128, WY, m.Z), dim3(128), 0, lm->stream, m, lm->ytab, WY);
     return GIE_OK;
 }
 
@@ -752,7 +760,7 @@ static void launch_xsweep(gie_locmap *lm, int WY, int *n_cols, int *slice_list, 
 {
     const XsLaunch &x = lm->xs;
     const BandCfg cfg{ x.NB, x.CAP, x.BW };
-    k_edt_xsweep<<<lm->xs_ctas, x.threads, x.smem, lm->stream>>>(lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices, lm->g2, lm->cxy,
+    gie_launch(k_edt_xsweep, dim3(lm->xs_ctas), dim3(x.threads), x.smem, lm->stream, lm->d, lm->ytab, WY, lm->col_list, n_cols, slice_list, n_slices, lm->g2, lm->cxy,
                                                                 cfg, lm->work_counters + 0, lm->edt_compact ? 1 : 0);
 }
 
@@ -765,11 +773,11 @@ static void launch_zsweep(gie_locmap *lm, const LocDev &m, int *slice_list, int 
     const int n_items = m.ysn * XG;
     if (lm->zs_banded) {
         const BandCfg cfg{ lm->zs.NB, lm->zs.CAP, lm->zs.BW };
-        k_edt_zsweep_banded<<<lm->zs_ctas, lm->zs.threads, lm->zs.smem, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, cfg,
+        gie_launch(k_edt_zsweep_banded, dim3(lm->zs_ctas), dim3(lm->zs.threads), lm->zs.smem, lm->stream, m, lm->g2, lm->cxy, slice_list, n_slices, cfg,
                                                                                      lm->work_counters + 2);
         lm->launches++;
     }
-    k_edt_zsweep<<<lm->edt_ctas, ZS_WARPS * 32, 0, lm->stream>>>(m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
+    gie_launch(k_edt_zsweep, dim3(lm->edt_ctas), dim3(ZS_WARPS * 32), 0, lm->stream, m, lm->g2, lm->cxy, slice_list, n_slices, (uint2 *)lm->stack_scratch, L,
                                                                  lm->work_counters + 1, n_items, XG, lm->zs_banded ? 1 : 0);
     lm->launches++;
 }
@@ -783,8 +791,8 @@ int gie_launch_edt_xy(gie_locmap *lm)
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     launch_ybits(lm, WY);
-    k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
-    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
     launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
     lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
@@ -796,7 +804,7 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
     if (max_width_override > 0) m.max_width = max_width_override;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
-    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
     launch_zsweep(lm, m, slice_list, n_slices);
     lm->launches += 1;
     GIE_CUDA_CHECK(cudaGetLastError());
@@ -830,8 +838,8 @@ int gie_launch_edt_pack(gie_locmap *lm, unsigned long long *ytab_compact, int *c
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     StageTimer t(lm, GIE_ST_EDT_PACK);
     launch_ybits(lm, WY);
-    k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
-    k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
     lm->launches += 3;
     if (ytab_compact && col_compact) {
         k_edt_compact<<<dim3(lm->num_sms, 8), 256, 0, lm->stream>>>(lm->ytab, lm->col_list, slice_list, n_slices, WY, m.X, ytab_compact, col_compact);
@@ -870,8 +878,8 @@ int gie_launch_batch_edt(gie_locmap *lm)
     {
         StageTimer t(lm, GIE_ST_EDT_PACK);
         launch_ybits(lm, WY);
-        k_edt_ycols<<<m.Z, ((m.X + 31) / 32) * 32, 0, lm->stream>>>(m, lm->ytab, WY, lm->col_list, n_cols);
-        k_edt_slices<<<1, ((m.Z + 31) / 32) * 32, 0, lm->stream>>>(m.Z, n_cols, slice_list, n_slices);
+        gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+        gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_X);

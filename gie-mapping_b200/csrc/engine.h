@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/gie_b200.h"
+#include <cstdlib>
 #include <string>
 
 struct XsLaunch { int rpi = 32, threads = 0, NB = 0, CAP = 0, BW = 0; size_t smem = 0; };   // launch shape of a banded sweep (edt.cu)
@@ -101,6 +102,28 @@ void gie_set_error(const std::string &msg);
             return GIE_ERR_CUDA;                                                                       \
         }                                                                                              \
     } while (0)
+
+// Per-frame kernels are launched with programmatic dependent launch: the next kernel's CTAs are placed while the previous
+// kernel drains, and wait (griddepcontrol.wait, the first statement of every such kernel — before any early return, so that the
+// dependency chain stays transitive) until it has completed and its memory operations are visible.  20 kernel boundaries per
+// frame otherwise cost a drain + launch each.  GIE_NO_PDL=1 falls back to plain stream order (the device-side instructions
+// are no-ops then).
+inline bool gie_pdl_enabled()
+{
+    static const bool on = getenv("GIE_NO_PDL") == nullptr;
+    return on;
+}
+template <typename... KArgs, typename... Args>
+inline void gie_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = gie_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface in the caller's cudaGetLastError check
+}
 
 struct StageTimer {
     gie_locmap *lm; int st;

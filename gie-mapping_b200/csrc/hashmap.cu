@@ -18,6 +18,7 @@ namespace {
 
 __global__ void k_build_btab(HashDev h, int entries)
 {
+    gie_pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= entries) return;
     int3 t = make_int3(i % h.tab_dim.x, (i / h.tab_dim.x) % h.tab_dim.y, i / (h.tab_dim.x * h.tab_dim.y));
@@ -96,6 +97,7 @@ __device__ __forceinline__ bool ext_obs_flag(const LocDev &m, int3 glb, int n_ob
 
 __global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int lane = threadIdx.x & 31;
     const int padded = (entries + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, 
 __global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_pvt, int3 tab_org, int3 tab_dim, const int *__restrict__ list,
                                                            const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
@@ -137,6 +140,7 @@ template <bool PNTCLD>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
                                                    const int *__restrict__ list, const int *__restrict__ count)
 {
+    gie_pdl_sync();
     using barrier_t = cuda::barrier<cuda::thread_scope_block>;
     __shared__ int s_blk;
     __shared__ alignas(16) int8_t s_type[512];
@@ -294,7 +298,7 @@ int gie_hash_begin_frame(gie_hashmap *hm)
     hm->d.tab_org = gie_vb_key(lm->d.pvt) - make_int3(hm->halo_blocks, hm->halo_blocks, hm->halo_blocks);
     int entries = (int)hm->tab_entries;
     GIE_CUDA_CHECK(cudaMemsetAsync(hm->d.touched, 0, hm->tab_entries, lm->stream));
-    k_build_btab<<<(entries + 255) / 256, 256, 0, lm->stream>>>(hm->d, entries);
+    gie_launch(k_build_btab, dim3((entries + 255) / 256), dim3(256), 0, lm->stream, hm->d, entries);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -310,7 +314,7 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     // and after a test upload), then list the blocks of this merge into the other buffer
     gie_hashmap::BlockList &prev = hm->blists[hm->bl_cur];
     if (prev.valid && !lm->glb_type_foreign) {
-        k_clear_prev_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
+        gie_launch(k_clear_prev_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
         lm->launches++;
     } else GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));
     lm->glb_type_foreign = false;
@@ -319,10 +323,10 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     gie_hashmap::BlockList &cur = hm->blists[hm->bl_cur];
     cur.valid = true; cur.pvt = lm->d.pvt; cur.tab_org = hm->d.tab_org;
     GIE_CUDA_CHECK(cudaMemsetAsync(cur.count, 0, sizeof(int), lm->stream));
-    k_list_merge_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, cur.list, cur.count);
+    gie_launch(k_list_merge_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, cur.list, cur.count);
     const int grid = lm->num_sms * 16;
-    if (input_pntcld) k_merge_ogm<true><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
-    else k_merge_ogm<false><<<grid, 256, 0, lm->stream>>>(lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
+    if (input_pntcld) gie_launch(k_merge_ogm<true>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
+    else gie_launch(k_merge_ogm<false>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
     lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;

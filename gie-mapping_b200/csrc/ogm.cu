@@ -38,6 +38,7 @@ __device__ __forceinline__ float3 coord2pos(const LocDev &m, int3 c)
 // registerLocObs (pntcld_raycast.cu:83-102)
 __global__ void k_pc_register(LocDev m, HashDev h, const float *__restrict__ pts, int n)
 {
+    gie_pdl_sync();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float3 p = make_float3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
                                                  RayCk *__restrict__ ck, float4 *__restrict__ incs, int *__restrict__ nsteps,
                                                  int *__restrict__ stop)
 {
+    gie_pdl_sync();
     __shared__ int origin_dec;
     if (threadIdx.x == 0) origin_dec = 0;
     __syncthreads();
@@ -169,6 +171,7 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
 __global__ void __launch_bounds__(128) k_pc_scan(LocDev m, int n, int max_segs, const RayCk *__restrict__ ck,
                                                  const float4 *__restrict__ incs, const int *__restrict__ nsteps, int *__restrict__ stop)
 {
+    gie_pdl_sync();
     const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int total = __ldg(&nsteps[i]), first = seg * RAY_SEG;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(128) k_pc_scan(LocDev m, int n, int max_segs, 
 __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, int max_segs, const RayCk *__restrict__ ck,
                                                   const float4 *__restrict__ incs, const int *__restrict__ stop)
 {
+    gie_pdl_sync();
     __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
     const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool use_win = seg == 0;                                  // uniform in the CTA
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, in
 // robot sphere of getAllocKeys (pntcld_raycast.cu:33-41): count = -1 inside the sphere, after the ray casting
 __global__ void k_pc_sphere(LocDev m, HashDev h, int r2, int r)
 {
+    gie_pdl_sync();
     int side = 2 * r + 1;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= side * side * side) return;
@@ -270,6 +275,7 @@ struct SensorParam {
 template <int SENSOR>
 __global__ void __launch_bounds__(256) k_projective(LocDev m, HashDev h, const float *__restrict__ data, SensorParam sp, int fmp, int r2)
 {
+    gie_pdl_sync();
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y, z = blockIdx.z;
     if (x >= m.X) return;
@@ -328,7 +334,7 @@ int launch_projective(gie_locmap *lm, gie_hashmap *hm, const float *data, const 
     StageTimer t(lm, GIE_ST_OGM);
     dim3 block(256), grid((lm->d.X + 255) / 256, lm->d.Y, lm->d.Z);
     if (lm->d.X <= 128) { block = dim3(128); grid.x = (lm->d.X + 127) / 128; }
-    k_projective<SENSOR><<<grid, block, 0, lm->stream>>>(lm->d, hm->d, data, sp, fmp, r2);
+    gie_launch(k_projective<SENSOR>, dim3(grid), dim3(block), 0, lm->stream, lm->d, hm->d, data, sp, fmp, r2);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -398,7 +404,7 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
     StageTimer t(lm, GIE_ST_OGM);
     if (n > 0) {
         int blocks = (n + 255) / 256;
-        k_pc_register<<<blocks, 256, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n);
+        gie_launch(k_pc_register, dim3(blocks), dim3(256), 0, lm->stream, lm->d, hm->d, pts_dev, n);
         // pntcld_raycast.cu:79: 0.707f*loc_map._local_size.x*loc_map._voxel_width
         float max_len = 0.707f * (float)lm->d.X * lm->d.w;
         // a walk crosses at most (|dx| + |dy| + |dz|) <= sqrt(3) voxel borders per voxel of length: bound on the segments of a ray
@@ -415,16 +421,16 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
         int *nsteps = (int *)(incs + n);
         int *stop = nsteps + n;
         const dim3 grid2((n + 127) / 128, max_segs);
-        k_pc_walk<<<(n + 127) / 128, 128, 0, lm->stream>>>(lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, incs, nsteps, stop);
-        k_pc_scan<<<grid2, 128, 0, lm->stream>>>(lm->d, n, max_segs, ck, incs, nsteps, stop);
-        k_pc_apply<<<grid2, 128, 0, lm->stream>>>(lm->d, hm->d, n, max_segs, ck, incs, stop);
+        gie_launch(k_pc_walk, dim3((n + 127) / 128), dim3(128), 0, lm->stream, lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, incs, nsteps, stop);
+        gie_launch(k_pc_scan, dim3(grid2), dim3(128), 0, lm->stream, lm->d, n, max_segs, ck, incs, nsteps, stop);
+        gie_launch(k_pc_apply, dim3(grid2), dim3(128), 0, lm->stream, lm->d, hm->d, n, max_segs, ck, incs, stop);
         lm->launches += 4;
     }
     if (fmp) {
         int r = 0;
         while (r * r <= r2) r++;
         int side = 2 * r + 1, tot = side * side * side;
-        k_pc_sphere<<<(tot + 255) / 256, 256, 0, lm->stream>>>(lm->d, hm->d, r2, r);
+        gie_launch(k_pc_sphere, dim3((tot + 255) / 256), dim3(256), 0, lm->stream, lm->d, hm->d, r2, r);
         lm->launches++;
     }
     GIE_CUDA_CHECK(cudaGetLastError());

@@ -114,6 +114,7 @@ __device__ __forceinline__ bool q_push(T *q, int *cnt, int cap, T v, int *status
 // block per CTA pass (hash pools are then read as 512 consecutive entries per field).
 __global__ void __launch_bounds__(256) k_list_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int lane = threadIdx.x & 31;
     const int padded = (entries + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
@@ -148,6 +149,7 @@ __device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev
 // stale, :258-261).
 __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ list, const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     const int mw = m.max_width;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
@@ -249,6 +251,7 @@ __device__ __forceinline__ void frontier_voxel(const LocDev &m, const HashDev &h
 __global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct, const int *__restrict__ list,
                                                    const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
@@ -796,6 +799,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) k_waves(LocDev m, HashDev h, 
 // UpdateHashBatch (unify_helper.cuh:448-523), one allocated block per CTA pass (see k_list_blocks)
 __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int *__restrict__ list, const int *__restrict__ count)
 {
+    gie_pdl_sync();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
@@ -826,6 +830,7 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display
 
 __global__ void k_wave_stats(WaveDev w, const int *status, long long *out)
 {
+    gie_pdl_sync();
     out[8] = *status;   // sticky device status, read by the next frame's entry points without a synchronisation
     out[0] = w.cnt[C_FA]; out[1] = w.cnt[C_FB]; out[2] = w.cnt[C_FC]; out[3] = w.cnt[C_LEVA]; out[4] = w.cnt[C_LEVB];
     out[5] = w.cnt[C_LEVC]; out[6] = w.cnt[C_FB_AFTER_A]; out[7] = w.cnt[C_FC_AFTER_B];
@@ -916,7 +921,7 @@ int gie_wave_list_blocks(gie_hashmap *hm)
     gie_locmap *lm = hm->lm;
     const int entries = (int)hm->tab_entries;
     GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
-    k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(lm->d, hm->d, entries, hm->blk_list, hm->blk_count);
+    gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, hm->blk_list, hm->blk_count);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -935,9 +940,9 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, hm->barrier_words * sizeof(unsigned int), lm->stream));
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
         const int entries = (int)hm->tab_entries;
-        k_list_blocks<<<std::min((entries + 255) / 256, lm->num_sms * 8), 256, 0, lm->stream>>>(m, hm->d, entries, hm->blk_list, hm->blk_count);
-        k_mark_blocks<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, hm->blk_list, hm->blk_count);
-        k_frontiers<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
+        gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, m, hm->d, entries, hm->blk_list, hm->blk_count);
+        gie_launch(k_mark_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, hm->blk_list, hm->blk_count);
+        gie_launch(k_frontiers, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
     }
     {
         StageTimer t(lm, GIE_ST_WAVES);
@@ -965,9 +970,9 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        k_commit<<<lm->num_sms * 8, 256, 0, lm->stream>>>(m, hm->d, display, hm->blk_list, hm->blk_count);
+        gie_launch(k_commit, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, display, hm->blk_list, hm->blk_count);
     }
-    k_wave_stats<<<1, 1, 0, lm->stream>>>(w, hm->d.status, hm->stats_host);
+    gie_launch(k_wave_stats, dim3(1), dim3(1), 0, lm->stream, w, hm->d.status, hm->stats_host);
     lm->launches += 6;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
