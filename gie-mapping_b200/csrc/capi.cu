@@ -54,7 +54,7 @@ int check_frame_args(gie_locmap *lm, gie_hashmap *hm)
     return GIE_OK;
 }
 
-// The device status word is sticky and is mirrored into pinned host memory at the end of every merge (k_wave_stats), so the
+// The device status word is sticky and is mirrored into pinned host memory at the end of every merge (tail of k_commit), so the
 // per-frame entry points can refuse to go on after the block pool ran out WITHOUT a device synchronisation.  The reference
 // throws "out of block memory" from its host-side allocator at once (blockalloc.h:56-58); here the failure surfaces on the
 // next call after the frame that hit it, and gie_sync() reports it immediately.
@@ -127,6 +127,7 @@ int gie_locmap_create(gie_locmap **out, float voxel_size, int X, int Y, int Z, u
     GIE_CUDA_CHECK(cudaMalloc(&m.coc_aux, n * 4));
     GIE_CUDA_CHECK(cudaMalloc(&m.wave_layer, n * 4));
     GIE_CUDA_CHECK(cudaMalloc(&m.pair, n * 8));
+    GIE_CUDA_CHECK(cudaMalloc(&m.nbr_flag, n));
     GIE_CUDA_CHECK(cudaMemset(m.ray_count, 0, n * 4));
     GIE_CUDA_CHECK(cudaMemset(m.inst_type, 0, n));
     GIE_CUDA_CHECK(cudaMemset(m.glb_type, 0, n));
@@ -135,6 +136,7 @@ int gie_locmap_create(gie_locmap **out, float voxel_size, int X, int Y, int Z, u
     GIE_CUDA_CHECK(cudaMemset(m.coc_aux, 0, n * 4));
     GIE_CUDA_CHECK(cudaMemset(m.wave_layer, 0, n * 4));
     GIE_CUDA_CHECK(cudaMemset(m.pair, 0, n * 8));
+    GIE_CUDA_CHECK(cudaMemset(m.nbr_flag, 0, n));
     int rc = gie_edt_prepare(lm);
     if (rc != GIE_OK) return rc;
     const float q[4] = { 1.f, 0.f, 0.f, 0.f }, t[3] = { 0.f, 0.f, 0.f };
@@ -148,7 +150,7 @@ int gie_locmap_destroy(gie_locmap *lm)
     cudaStreamSynchronize(lm->stream);
     LocDev &m = lm->d;
     cudaFree(m.ray_count); cudaFree(m.inst_type); cudaFree(m.glb_type); cudaFree(m.edt); cudaFree(m.aux);
-    cudaFree(m.coc_aux); cudaFree(m.wave_layer); cudaFree(m.pair);
+    cudaFree(m.coc_aux); cudaFree(m.wave_layer); cudaFree(m.pair); cudaFree(m.nbr_flag);
     if (!lm->edt_inputs_aliased) { cudaFree(lm->ytab); cudaFree(lm->col_list); cudaFree(lm->edt_meta); }
     cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
     for (int i = 0; i < lm->n_ipc_opened; i++) cudaIpcCloseMemHandle(lm->ipc_opened[i]);
@@ -366,8 +368,9 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     cudaFree(h.occ_val); cudaFree(h.vox_type); cudaFree(h.update_ct); cudaFree(h.coc_glb); cudaFree(h.dist_sq);
     cudaFree(h.wave_layer); cudaFree(h.pair); cudaFree(h.btab); cudaFree(h.touched); for (auto &bl : hm->blists) { cudaFree(bl.list); cudaFree(bl.count); } cudaFree(h.dirty); cudaFree(hm->changed_list); cudaFree(hm->changed_count); cudaFree(hm->obs_dev);
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
-    cudaFree(hm->cseed_key); cudaFree(hm->counters); cudaFree(hm->barrier); cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
-    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list); cudaFree(hm->blk_count);
+    cudaFree(hm->cseed_key); cudaFree(hm->barrier);   // counters and blk_count live inside the barrier allocation
+    cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
+    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list);
     cudaFreeHost(hm->status_host); cudaFreeHost(hm->stats_host);
     if (hm->lm->hm == hm) hm->lm->hm = nullptr;
     delete hm;

@@ -56,6 +56,8 @@ struct LocDev {
     int32_t *coc_aux;   // batch coc, local coords packed 11/11/10     == reference _coc_idx_aux
     int32_t *wave_layer;
     unsigned long long *pair;  // (dist_sq << 32) | wave-range coc id  == reference _dist_id_pair
+    uint8_t *nbr_flag;         // 1 = the closest obstacle of this known voxel lies outside the local volume but inside the wave range
+                               // (written with the pair by k_mark_blocks; k_frontiers tests it for six neighbours instead of decoding six pairs)
     // --- volumes sharded over GPUs ---
     // A slab map holds rows [ys0, ys0 + ysn) of the batch-EDT arrays (g2, cxy, aux, coc_aux are [Z][ysn][X]); the sweeps
     // take their work items from that range.  A whole map has ys0 = 0, ysn = Y.

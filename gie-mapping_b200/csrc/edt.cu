@@ -142,9 +142,10 @@ __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long
 
 // ordered list of the slices that hold at least one obstacle
 __global__ void __launch_bounds__(1024) k_edt_slices(int Z, const int *__restrict__ n_cols, int *__restrict__ slice_list,
-                                                     int *__restrict__ n_slices)
+                                                     int *__restrict__ n_slices, int *__restrict__ zero4)
 {
     gie_pdl_sync();
+    if (zero4 && threadIdx.x < 4) zero4[threadIdx.x] = 0;   // the sweeps' work counters (saves a memset node per frame)
     __shared__ int warp_cnt[32];
     const int z = threadIdx.x, lane = z & 31, wid = z >> 5;
     bool any = z < Z && n_cols[z] > 0;
@@ -792,7 +793,7 @@ int gie_launch_edt_xy(gie_locmap *lm)
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     launch_ybits(lm, WY);
     gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
-    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, (int *)nullptr);
     launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
     lm->launches += 4;
     GIE_CUDA_CHECK(cudaGetLastError());
@@ -804,7 +805,7 @@ int gie_launch_edt_z(gie_locmap *lm, int max_width_override)
     if (max_width_override > 0) m.max_width = max_width_override;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
-    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, (int *)nullptr);
     launch_zsweep(lm, m, slice_list, n_slices);
     lm->launches += 1;
     GIE_CUDA_CHECK(cudaGetLastError());
@@ -839,7 +840,7 @@ int gie_launch_edt_pack(gie_locmap *lm, unsigned long long *ytab_compact, int *c
     StageTimer t(lm, GIE_ST_EDT_PACK);
     launch_ybits(lm, WY);
     gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
-    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
+    gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, (int *)nullptr);
     lm->launches += 3;
     if (ytab_compact && col_compact) {
         k_edt_compact<<<dim3(lm->num_sms, 8), 256, 0, lm->stream>>>(lm->ytab, lm->col_list, slice_list, n_slices, WY, m.X, ytab_compact, col_compact);
@@ -874,12 +875,11 @@ int gie_launch_batch_edt(gie_locmap *lm)
     const LocDev &m = lm->d;
     const int WY = (m.Y + 31) / 32;
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
-    GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     {
         StageTimer t(lm, GIE_ST_EDT_PACK);
         launch_ybits(lm, WY);
         gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
-        gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices);
+        gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, lm->work_counters);
     }
     {
         StageTimer t(lm, GIE_ST_EDT_X);

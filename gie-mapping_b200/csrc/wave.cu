@@ -24,7 +24,7 @@ constexpr int WAVE_THREADS = 512;   // one CTA per SM: the grid barrier costs gr
 
 // counters layout (ints)
 enum { C_A0 = 0, C_B0 = 3, C_C0 = 6, C_LEVA = 10, C_LEVB = 11, C_LEVC = 12, C_FA = 13, C_FB = 14, C_FC = 15,
-       C_FB_AFTER_A = 16, C_FC_AFTER_B = 17, C_CUR_LEVEL = 18, C_COUNT = 32 };
+       C_FB_AFTER_A = 16, C_FC_AFTER_B = 17, C_CUR_LEVEL = 18, C_DONE = 19, C_COUNT = 32 };
 
 // cluster-local mode of wave C (see wave_c_local): per-CTA frontier queues in shared memory
 constexpr int LQ_CAP = 2048;
@@ -178,6 +178,10 @@ __global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const 
                 if (!have_id) pid = gie_pair_id(m.pair[id]);     // stale id word
             } else { pdist = aux; pid = gie_wr2id(wr); }
             m.pair[id] = gie_mk_pair(pdist, pid);
+            {   // what k_frontiers asks of a NEIGHBOUR's pair (unify_helper.cuh:300-312), answered once here
+                const int3 fwr = gie_id2wr(pid), fcb = fwr + m.upvt - m.pvt;
+                m.nbr_flag[id] = (!gie_inside_loc(m, fcb) && gie_inside_wr(fwr)) ? 1 : 0;
+            }
             if (aux != dist_new) *paux = aux;
         }
     }
@@ -201,9 +205,9 @@ __device__ __forceinline__ void frontier_voxel(const LocDev &m, const HashDev &h
             if (gie_inside_loc(m, nb)) {
                 int nid = gie_lidx(m, nb);
                 if (m.glb_type[nid] == GIE_VOX_UNKNOWN) { nbr_unknown = true; continue; }
-                int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
-                int3 ncb = nwr + m.upvt - m.pvt;
-                if (!gie_inside_loc(m, ncb) && gie_inside_wr(nwr)) {
+                if (m.nbr_flag[nid]) {                   // its closest obstacle is outside the volume and inside the wave range (rare)
+                    int3 nwr = gie_id2wr(gie_pair_id(m.pair[nid]));
+                    int3 ncb = nwr + m.upvt - m.pvt;
                     int d2 = sqd3(ncb, c);
                     if (d2 < cur_dist) { new_key = gie_mk_pair(d2, gie_wr2id(nwr)); lowered = true; }
                 }
@@ -797,7 +801,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) k_waves(LocDev m, HashDev h, 
 }
 
 // UpdateHashBatch (unify_helper.cuh:448-523), one allocated block per CTA pass (see k_list_blocks)
-__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int *__restrict__ list, const int *__restrict__ count)
+__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int *__restrict__ list, const int *__restrict__ count,
+                                                int *cnt, long long *stats_out)
 {
     gie_pdl_sync();
     const int n = __ldcg(count);
@@ -826,14 +831,19 @@ __global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display
             if (type == GIE_VOX_FNT) h.vox_type[vi] = GIE_VOX_FNT;
         }
     }
-}
-
-__global__ void k_wave_stats(WaveDev w, const int *status, long long *out)
-{
-    gie_pdl_sync();
-    out[8] = *status;   // sticky device status, read by the next frame's entry points without a synchronisation
-    out[0] = w.cnt[C_FA]; out[1] = w.cnt[C_FB]; out[2] = w.cnt[C_FC]; out[3] = w.cnt[C_LEVA]; out[4] = w.cnt[C_LEVB];
-    out[5] = w.cnt[C_LEVC]; out[6] = w.cnt[C_FB_AFTER_A]; out[7] = w.cnt[C_FC_AFTER_B];
+    // the last CTA to finish publishes the frame's wavefront statistics and the sticky device status to pinned host memory
+    // (read by the next frame's entry points without a synchronisation); this was a one-thread kernel of its own
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&cnt[C_DONE], 1) == (int)gridDim.x - 1) {
+            __threadfence();
+            stats_out[8] = *(volatile int *)h.status;
+            stats_out[0] = __ldcg(&cnt[C_FA]); stats_out[1] = __ldcg(&cnt[C_FB]); stats_out[2] = __ldcg(&cnt[C_FC]);
+            stats_out[3] = __ldcg(&cnt[C_LEVA]); stats_out[4] = __ldcg(&cnt[C_LEVB]); stats_out[5] = __ldcg(&cnt[C_LEVC]);
+            stats_out[6] = __ldcg(&cnt[C_FB_AFTER_A]); stats_out[7] = __ldcg(&cnt[C_FC_AFTER_B]);
+        }
+    }
 }
 
 WaveDev make_wave_dev(gie_hashmap *hm)
@@ -872,7 +882,6 @@ int gie_wave_prepare(gie_hashmap *hm)
         GIE_CUDA_CHECK(cudaMalloc(&hm->qC[i], cap * 8));
     }
     GIE_CUDA_CHECK(cudaMalloc(&hm->cseed_key, cap * 8));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->counters, C_COUNT * sizeof(int)));
     int per_sm = 0;
     GIE_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_waves, WAVE_THREADS, 0));
     if (per_sm < 1) { gie_set_error("wave kernel does not fit on an SM"); return GIE_ERR_CUDA; }
@@ -900,14 +909,17 @@ int gie_wave_prepare(gie_hashmap *hm)
     }
     // sized for the larger of the cluster grid and the plain one-CTA-per-SM grid the launch falls back to (gie_launch_merge)
     hm->barrier_words = (size_t)(std::max(hm->wave_ctas, lm->num_sms) + 1) * 32;
-    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, hm->barrier_words * sizeof(unsigned int)));
+    // barrier lines, wave counters and the block-list counter share one allocation: one memset per frame clears all three
+    static_assert(C_COUNT <= 64, "wave counters outgrew their slot");
+    GIE_CUDA_CHECK(cudaMalloc(&hm->barrier, (hm->barrier_words + 64 + 32) * sizeof(unsigned int)));
+    hm->counters = (int *)(hm->barrier + hm->barrier_words);
+    hm->blk_count = hm->counters + 64;
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_dist, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_coc, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_pair, cap * 8));
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_flags, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->snap_id, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->blk_list, hm->tab_entries * sizeof(int)));
-    GIE_CUDA_CHECK(cudaMalloc(&hm->blk_count, sizeof(int)));
     if (getenv("GIE_WAVE_TRACE")) {
         GIE_CUDA_CHECK(cudaMalloc(&hm->wave_trace, (size_t)TRACE_LEVELS * 10 * 8));
         GIE_CUDA_CHECK(cudaMemset(hm->wave_trace, 0, (size_t)TRACE_LEVELS * 10 * 8));
@@ -936,9 +948,7 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     w.display = display;
     {
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
-        GIE_CUDA_CHECK(cudaMemsetAsync(hm->counters, 0, C_COUNT * sizeof(int), lm->stream));
-        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, hm->barrier_words * sizeof(unsigned int), lm->stream));
-        GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
+        GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, (hm->barrier_words + 64 + 32) * sizeof(unsigned int), lm->stream));   // + counters + blk_count
         const int entries = (int)hm->tab_entries;
         gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, m, hm->d, entries, hm->blk_list, hm->blk_count);
         gie_launch(k_mark_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, hm->blk_list, hm->blk_count);
@@ -970,10 +980,9 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        gie_launch(k_commit, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, display, hm->blk_list, hm->blk_count);
+        gie_launch(k_commit, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, display, hm->blk_list, hm->blk_count, hm->counters, hm->stats_host);
     }
-    gie_launch(k_wave_stats, dim3(1), dim3(1), 0, lm->stream, w, hm->d.status, hm->stats_host);
-    lm->launches += 6;
+    lm->launches += 5;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
 }
