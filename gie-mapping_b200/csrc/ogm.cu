@@ -61,12 +61,12 @@ __global__ void k_pc_register(LocDev m, HashDev h, const float *__restrict__ pts
 // per SM.  The walk itself is pure arithmetic, so it is split off:
 //   k_pc_walk  : thread = ray.  Runs the DDA without touching memory — the same float operations in the same order as
 //                ray_cast.h:104-143, so every visited voxel is the reference's — and checkpoints its state every RAY_SEG steps.
-//   k_pc_scan  : thread = (ray, segment).  Replays the segment from its checkpoint, loads the types of its voxels (RAY_SEG
-//                independent loads) and records the first OCCUPIED one: the ray stops there (clearRayLoc returns false).
-//   k_pc_apply : thread = (ray, segment).  Replays again and decrements every in-volume voxel before the stop.
+//   k_pc_apply : thread = (ray, segment).  Replays the segment from its checkpoint twice: once loading the types of its voxels
+//                (RAY_SEG independent loads) to find the first OCCUPIED one, once decrementing every in-volume voxel before it.
+//   k_pc_undo  : thread = (ray, segment).  Segments that turn out to lie behind their ray's stop give back what they took.
 // ~20x the threads, every load and atomic independent of the others; the visited set and the counts are unchanged.
-// (Folding the scan into the walk — the walk thread loads the types of a segment and looks at them one segment later — measured
-// slower: 0.23 ms for the stage against 0.13, the loads lengthen the one dependent chain that bounds the kernel.)
+// (Folding the type loads into the walk — the walk thread loads the types of a segment and looks at them one segment later —
+// measured slower: 0.23 ms for the stage against 0.13, the loads lengthen the one dependent chain that bounds the kernel.)
 // Every ray starts at the sensor, so the voxels around the origin are decremented by all rays: the CTAs of the first segment
 // accumulate the decrements that fall into a WIN^3 window around the origin voxel in shared memory and flush the window once
 // (sums commute, the result is identical).
@@ -97,7 +97,7 @@ __device__ __forceinline__ void ray_setup(const LocDev &m, const float *__restri
     if (r.sy != 0) { float b = (float)r.p0i.y * m.w + (float)r.sy * m.w * 0.5f; r.tmy = (b - r.p0.y) / dy; r.tdy = m.w / fabsf(dy); }
     if (r.sz != 0) { float b = (float)r.p0i.z * m.w + (float)r.sz * m.w * 0.5f; r.tmz = (b - r.p0.z) / dz; r.tdz = m.w / fabsf(dz); }
 }
-// What a DDA step needs of the set-up: k_pc_walk stores it per ray (16 bytes), the (ray, segment) threads of k_pc_scan /
+// What a DDA step needs of the set-up: k_pc_walk stores it per ray (16 bytes), the (ray, segment) threads of
 // k_pc_apply load it instead of redoing the set-up's six IEEE divisions and the square root.
 struct RayInc { float tdx, tdy, tdz; int sx, sy, sz; };
 __device__ __forceinline__ RayInc ray_inc(const RaySetup &r) { return RayInc{ r.tdx, r.tdy, r.tdz, r.sx, r.sy, r.sz }; }
@@ -167,38 +167,15 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
     }
 }
 
-// thread = (ray, segment); CTAs are segment-major so that all threads of a CTA work on the same segment index
-__global__ void __launch_bounds__(128) k_pc_scan(LocDev m, int n, int max_segs, const RayCk *__restrict__ ck,
-                                                 const float4 *__restrict__ incs, const int *__restrict__ nsteps, int *__restrict__ stop)
-{
-    gie_pdl_sync();
-    const int seg = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int total = __ldg(&nsteps[i]), first = seg * RAY_SEG;
-    if (first >= total) return;
-    const RayInc r = ray_inc_unpack(__ldg(&incs[i]));
-    const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
-    int3 cur = make_int3(c.x, c.y, c.z);
-    float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
-    const int cnt = min(RAY_SEG, total - first);
-    int8_t t[RAY_SEG];
-#pragma unroll
-    for (int j = 0; j < RAY_SEG; j++) {
-        t[j] = GIE_VOX_UNKNOWN;
-        if (j < cnt) {
-            ray_step(r, cur, tmx, tmy, tmz);
-            const int3 loc = cur - m.pvt;
-            if (gie_inside_loc(m, loc)) t[j] = m.inst_type[gie_lidx(m, loc)];
-        }
-    }
-    int hit = RAY_SEG;
-#pragma unroll
-    for (int j = RAY_SEG - 1; j >= 0; j--) if (t[j] == GIE_VOX_OCCUPIED) hit = j;
-    if (hit < cnt) atomicMin(&stop[i], first + hit);
-}
-
+// thread = (ray, segment); CTAs are segment-major so that all threads of a CTA work on the same segment index.
+// Pass 1 replays the segment and loads the types of its voxels (independent loads): the first OCCUPIED one is where the ray
+// would stop IF no earlier segment stops it (clearRayLoc returns false, pntcld_raycast.cu:9-18).  Pass 2 replays again and
+// decrements the voxels before that local stop — speculatively: a segment does not know yet whether an earlier one holds
+// the ray's real stop.  k_pc_undo puts back what the segments behind the real stop took (integer sums commute, so
+// ray_count ends bit-exact); rays stop where they end or a few voxels earlier, so it has little to do.  This replaces a scan
+// kernel and an apply kernel that each replayed every segment (2 x 20 x 440 CTAs per scan at 512^3).
 __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, int max_segs, const RayCk *__restrict__ ck,
-                                                  const float4 *__restrict__ incs, const int *__restrict__ stop)
+                                                  const float4 *__restrict__ incs, const int *__restrict__ nsteps, int *__restrict__ stop)
 {
     gie_pdl_sync();
     __shared__ int win[RAY_WIN * RAY_WIN * RAY_WIN];
@@ -211,15 +188,30 @@ __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, in
         __syncthreads();
     }
     const int first = seg * RAY_SEG;
-    const int last = i < n ? __ldg(&stop[i]) : 0;                    // steps [0, last) are decremented
-    if (i < n && first < last) {
+    const int total = i < n ? __ldg(&nsteps[i]) : 0;
+    if (first < total) {
         const RayInc r = ray_inc_unpack(__ldg(&incs[i]));
         const RayCk c = ck[(size_t)seg * n + i];   // segment-major: coalesced over the rays of a warp
+        const int cnt = min(RAY_SEG, total - first);
+        int hit = RAY_SEG;
+        {
+            int3 cur = make_int3(c.x, c.y, c.z);
+            float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
+#pragma unroll
+            for (int j = 0; j < RAY_SEG; j++) {
+                if (j < cnt) {
+                    ray_step(r, cur, tmx, tmy, tmz);
+                    const int3 loc = cur - m.pvt;
+                    if (gie_inside_loc(m, loc) && m.inst_type[gie_lidx(m, loc)] == GIE_VOX_OCCUPIED) hit = min(hit, j);
+                }
+            }
+        }
+        if (hit < cnt) atomicMin(&stop[i], first + hit);
+        const int lim = min(cnt, hit);
         int3 cur = make_int3(c.x, c.y, c.z);
         float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
-        const int cnt = min(RAY_SEG, last - first);
         int last_ti = -1;
-        for (int j = 0; j < cnt; j++) {
+        for (int j = 0; j < lim; j++) {
             ray_step(r, cur, tmx, tmy, tmz);
             const int3 loc = cur - m.pvt;
             if (!gie_inside_loc(m, loc)) continue;                   // the walk continues outside the volume (ray_cast.h:116-121)
@@ -239,6 +231,31 @@ __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, in
             const int3 loc = worg + make_int3(k % RAY_WIN, (k / RAY_WIN) % RAY_WIN, k / (RAY_WIN * RAY_WIN)) - m.pvt;
             atomicAdd(&m.ray_count[gie_lidx(m, loc)], v);            // only in-volume voxels were accumulated
         }
+    }
+}
+
+// the segments that lie entirely behind their ray's stop give back what they took (a block they touched stays flagged: the
+// merge looks at it and finds nothing observed)
+__global__ void __launch_bounds__(128) k_pc_undo(LocDev m, int n, int max_segs, const RayCk *__restrict__ ck, const float4 *__restrict__ incs,
+                                                 const int *__restrict__ nsteps, const int *__restrict__ stop)
+{
+    gie_pdl_sync();
+    const int seg = 1 + blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;   // segment 0 is never behind a stop
+    if (i >= n) return;
+    const int first = seg * RAY_SEG, total = __ldg(&nsteps[i]);
+    if (first >= total || first <= __ldg(&stop[i])) return;          // stop == first: the segment's own first voxel, nothing was taken
+    const RayInc r = ray_inc_unpack(__ldg(&incs[i]));
+    const RayCk c = ck[(size_t)seg * n + i];
+    const int cnt = min(RAY_SEG, total - first);
+    int3 cur = make_int3(c.x, c.y, c.z);
+    float tmx = c.tmx, tmy = c.tmy, tmz = c.tmz;
+    for (int j = 0; j < cnt; j++) {                                  // what pass 2 of k_pc_apply did: up to the segment's own first OCCUPIED voxel
+        ray_step(r, cur, tmx, tmy, tmz);
+        const int3 loc = cur - m.pvt;
+        if (!gie_inside_loc(m, loc)) continue;
+        const int id = gie_lidx(m, loc);
+        if (m.inst_type[id] == GIE_VOX_OCCUPIED) break;
+        atomicAdd(&m.ray_count[id], 1);
     }
 }
 
@@ -422,8 +439,8 @@ int gie_launch_ogm_pointcloud(gie_locmap *lm, gie_hashmap *hm, const float *pts_
         int *stop = nsteps + n;
         const dim3 grid2((n + 127) / 128, max_segs);
         gie_launch(k_pc_walk, dim3((n + 127) / 128), dim3(128), 0, lm->stream, lm->d, hm->d, pts_dev, n, max_len, max_segs, ck, incs, nsteps, stop);
-        gie_launch(k_pc_scan, dim3(grid2), dim3(128), 0, lm->stream, lm->d, n, max_segs, ck, incs, nsteps, stop);
-        gie_launch(k_pc_apply, dim3(grid2), dim3(128), 0, lm->stream, lm->d, hm->d, n, max_segs, ck, incs, stop);
+        gie_launch(k_pc_apply, dim3(grid2), dim3(128), 0, lm->stream, lm->d, hm->d, n, max_segs, ck, incs, nsteps, stop);
+        if (max_segs > 1) gie_launch(k_pc_undo, dim3((n + 127) / 128, max_segs - 1), dim3(128), 0, lm->stream, lm->d, n, max_segs, ck, incs, nsteps, stop);
         lm->launches += 4;
     }
     if (fmp) {
