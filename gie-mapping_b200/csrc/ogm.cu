@@ -172,8 +172,10 @@ __global__ void __launch_bounds__(128) k_pc_walk(LocDev m, HashDev h, const floa
 // would stop IF no earlier segment stops it (clearRayLoc returns false, pntcld_raycast.cu:9-18).  Pass 2 replays again and
 // decrements the voxels before that local stop — speculatively: a segment does not know yet whether an earlier one holds
 // the ray's real stop.  k_pc_undo puts back what the segments behind the real stop took (integer sums commute, so
-// ray_count ends bit-exact); rays stop where they end or a few voxels earlier, so it has little to do.  This replaces a scan
-// kernel and an apply kernel that each replayed every segment (2 x 20 x 440 CTAs per scan at 512^3).
+// ray_count ends bit-exact).  This replaces a scan kernel and an apply kernel that each replayed every segment; in the frame
+// the stage takes 0.104 ms against 0.107 (the undo pass overlaps the next kernel's launch), although the two kernels alone,
+// serialised under ncu, take 72 us against 56: rays that graze a nearer silhouette are stopped early and have several
+// segments to give back.  (Listing those rays and undoing them warp-per-ray was slower still: 0.121 ms for the stage.)
 __global__ void __launch_bounds__(128) k_pc_apply(LocDev m, HashDev h, int n, int max_segs, const RayCk *__restrict__ ck,
                                                   const float4 *__restrict__ incs, const int *__restrict__ nsteps, int *__restrict__ stop)
 {

@@ -3,3 +3,4 @@ mkdir -p gpurun_out
 tail -3 gpurun_out/pytest_subset.log
 timeout 600 python bench.py --steps 50 --warmup 10 --no-cpu-baseline --no-dense-case > gpurun_out/bench_cur.log 2>&1
 grep '^{' gpurun_out/bench_cur.log | python -c "import sys,json; d=json.loads(sys.stdin.readline()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('stage_ms'), d.get('gpu_launches'))"
+bash scratch/gpu_launch_list.sh | tail -22

@@ -8,7 +8,7 @@ def col(name): return hdr.index(name)
 def val(r, name):
     i = col(name)
     return float(r[i].replace(",", "")) * SC.get(units[i], 1.0)
-names = ['k_list_merge_blocks', 'k_build_btab', 'k_pc_register', 'k_pc_walk', 'k_pc_scan', 'k_pc_apply', 'k_pc_free', 'k_clear_prev_blocks', 'k_merge_ogm', 'k_alloc_observed',
+names = ['k_list_merge_blocks', 'k_build_btab', 'k_pc_register', 'k_pc_walk', 'k_pc_scan', 'k_pc_apply', 'k_pc_undo', 'k_pc_free', 'k_clear_prev_blocks', 'k_merge_ogm', 'k_alloc_observed',
          'k_edt_ybits_clear', 'k_edt_ybits_blocks', 'k_edt_ybits', 'k_edt_ycols', 'k_edt_slices', 'k_edt_xsweep', 'k_edt_zsweep_banded', 'k_edt_zsweep', 'k_list_blocks',
          'k_mark_blocks', 'k_mark', 'k_frontiers', 'k_waves', 'k_commit', 'k_wave_stats']
 per = {}
@@ -27,7 +27,7 @@ with open(out_csv, "w") as f:
         w.writerow([short, r[col('Grid Size')], r[col('Block Size')], f"{t:.2f}", int(rd), int(wr)] + [r[col(k)] for k in keep])
 grp = {"batch_dt": ["k_edt_ybits_clear", "k_edt_ybits_blocks", "k_edt_ybits", "k_edt_ycols", "k_edt_slices", "k_edt_xsweep", "k_edt_zsweep_banded", "k_edt_zsweep"],
        "edt_pack": ["k_edt_ybits_clear", "k_edt_ybits_blocks", "k_edt_ybits", "k_edt_ycols", "k_edt_slices"], "edt_x": ["k_edt_xsweep"], "edt_z": ["k_edt_zsweep_banded", "k_edt_zsweep"],
-       "ogm": ["k_pc_register", "k_pc_walk", "k_pc_scan", "k_pc_apply"], "hash_merge": ["k_build_btab", "k_clear_prev_blocks", "k_list_merge_blocks", "k_merge_ogm"],
+       "ogm": ["k_pc_register", "k_pc_walk", "k_pc_scan", "k_pc_apply", "k_pc_undo"], "hash_merge": ["k_build_btab", "k_clear_prev_blocks", "k_list_merge_blocks", "k_merge_ogm"],
        "mark_frontier": ["k_list_blocks", "k_mark", "k_mark_blocks", "k_frontiers"], "waves": ["k_waves"], "commit": ["k_commit"]}
 out = {g: sum(per[n]["dram_bytes"] for n in ns if n in per) for g, ns in grp.items()}
 out["_source"] = label
