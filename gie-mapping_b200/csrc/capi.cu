@@ -370,7 +370,7 @@ int gie_hashmap_destroy(gie_hashmap *hm)
     for (int i = 0; i < 3; i++) { cudaFree(hm->qA[i]); cudaFree(hm->qB[i]); cudaFree(hm->qC[i]); }
     cudaFree(hm->cseed_key); cudaFree(hm->barrier);   // counters and blk_count live inside the barrier allocation
     cudaFree(hm->decA_dist); cudaFree(hm->decA_coc);
-    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list);
+    cudaFree(hm->decA_pair); cudaFree(hm->decA_flags); cudaFree(hm->snap_id); cudaFree(hm->wave_trace); cudaFree(hm->blk_list); cudaFree(hm->blk_org);
     cudaFreeHost(hm->status_host); cudaFreeHost(hm->stats_host);
     if (hm->lm->hm == hm) hm->lm->hm = nullptr;
     delete hm;

@@ -79,6 +79,7 @@ struct gie_hashmap {
     int bl_cur = 0;
     long long merge_serial = 0;   // OGM merges done so far
     int *blk_list = nullptr;      // table indices of the allocated blocks that intersect the local volume (per merge)
+    int4 *blk_org = nullptr;      // per listed block: local coordinates of its first voxel, pool index
     int *blk_count = nullptr;
     int merge_epoch = 0;          // merges done so far; the seed mark of m.wave_layer (memset to 0 at creation)
     int wave_cluster = 1;         // CTAs per thread-block cluster of the wave kernel

@@ -112,30 +112,39 @@ __device__ __forceinline__ bool q_push(T *q, int *cnt, int cap, T v, int *status
 // of the whole volume: a known voxel always has a block, and in the headline scene the allocated blocks cover ~5 % of the
 // 512^3 volume.  k_list_blocks compacts the dense block table into that list once per merge; the kernels then take one
 // block per CTA pass (hash pools are then read as 512 consecutive entries per field).
-__global__ void __launch_bounds__(256) k_list_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int *__restrict__ count)
+// Next to the table index the list carries the local coordinates of the block's first voxel and its pool index: decoding a
+// table index takes two divisions and two remainders by run-time values, which the per-voxel kernels used to repeat for each
+// of a block's 512 voxels (a quarter of k_frontiers' instructions).
+__global__ void __launch_bounds__(256) k_list_blocks(LocDev m, HashDev h, int entries, int *__restrict__ list, int4 *__restrict__ org,
+                                                     int *__restrict__ count)
 {
     gie_pdl_sync();
     const int lane = threadIdx.x & 31;
     const int padded = (entries + 31) & ~31;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < padded; i += gridDim.x * blockDim.x) {
         bool take = false;
-        if (i < entries && __ldcg(&h.btab[i]) >= 0) {
+        int blk = -1;
+        int3 lo = make_int3(0, 0, 0);
+        if (i < entries && (blk = __ldcg(&h.btab[i])) >= 0) {
             int3 k = make_int3(i % h.tab_dim.x, (i / h.tab_dim.x) % h.tab_dim.y, i / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
-            int3 lo = make_int3(k.x * 8, k.y * 8, k.z * 8) - m.pvt;   // local coords of the block's first voxel
+            lo = make_int3(k.x * 8, k.y * 8, k.z * 8) - m.pvt;   // local coords of the block's first voxel
             take = lo.x + 7 >= 0 && lo.x < m.X && lo.y + 7 >= 0 && lo.y < m.Y && lo.z + 7 >= 0 && lo.z < m.Z;
         }
         unsigned bal = __ballot_sync(0xffffffffu, take);
         int base = 0;
         if (lane == 0 && bal) base = atomicAdd(count, __popc(bal));
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (take) list[base + __popc(bal & ((1u << lane) - 1))] = i;
+        if (take) {
+            const int at = base + __popc(bal & ((1u << lane) - 1));
+            list[at] = i;
+            org[at] = make_int4(lo.x, lo.y, lo.z, blk);
+        }
     }
 }
-// local coordinate of voxel v (engine order, x fastest) of the block at table index ti; false when outside the volume
-__device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev &h, int ti, int v, int3 &c)
+// local coordinate of voxel v (engine order, x fastest) of the block whose first voxel is at o; false when outside the volume
+__device__ __forceinline__ bool block_voxel_local(const LocDev &m, int4 o, int v, int3 &c)
 {
-    int3 k = make_int3(ti % h.tab_dim.x, (ti / h.tab_dim.x) % h.tab_dim.y, ti / (h.tab_dim.x * h.tab_dim.y)) + h.tab_org;
-    c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - m.pvt;
+    c = make_int3(o.x + (v & 7), o.y + ((v >> 3) & 7), o.z + (v >> 6));
     return gie_inside_loc(m, c);
 }
 
@@ -147,17 +156,17 @@ __device__ __forceinline__ bool block_voxel_local(const LocDev &m, const HashDev
 // where the batch EDT found something farther than the distance the global map remembers to an obstacle that has left the
 // volume, keep the remembered one; a coc outside the wave range invalidates the distance word only (the id word stays
 // stale, :258-261).
-__global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int *__restrict__ list, const int *__restrict__ count)
+__global__ void __launch_bounds__(256) k_mark_blocks(LocDev m, HashDev h, const int4 *__restrict__ org, const int *__restrict__ count)
 {
     gie_pdl_sync();
     const int n = __ldcg(count);
     const int mw = m.max_width;
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int ti = __ldcg(&list[b]);
-        const int blk = __ldcg(&h.btab[ti]);
+        const int4 o = __ldcg(&org[b]);
+        const int blk = o.w;
         for (int v = threadIdx.x; v < 512; v += blockDim.x) {
             int3 c;
-            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            if (!block_voxel_local(m, o, v, c)) continue;
             const int id = gie_lidx(m, c);
             if (m.glb_type[id] == GIE_VOX_UNKNOWN) continue;
             const size_t vi = (size_t)blk * 512 + v;
@@ -252,16 +261,16 @@ __device__ __forceinline__ void frontier_voxel(const LocDev &m, const HashDev &h
         if (type == GIE_VOX_FREE && nbr_unknown) m.glb_type[id] = GIE_VOX_FNT;
     }
 }
-__global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct, const int *__restrict__ list,
+__global__ void __launch_bounds__(256) k_frontiers(LocDev m, HashDev h, WaveDev w, int map_ct, const int4 *__restrict__ org,
                                                    const int *__restrict__ count)
 {
     gie_pdl_sync();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int ti = __ldcg(&list[b]);
+        const int4 o = __ldcg(&org[b]);
         for (int v = threadIdx.x; v < 512; v += blockDim.x) {
             int3 c;
-            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            if (!block_voxel_local(m, o, v, c)) continue;
             const int id = gie_lidx(m, c);
             const int8_t type = m.glb_type[id];
             if (type != GIE_VOX_UNKNOWN) frontier_voxel(m, h, w, map_ct, c, id, type);
@@ -801,17 +810,17 @@ __global__ void __launch_bounds__(WAVE_THREADS, 1) k_waves(LocDev m, HashDev h, 
 }
 
 // UpdateHashBatch (unify_helper.cuh:448-523), one allocated block per CTA pass (see k_list_blocks)
-__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int *__restrict__ list, const int *__restrict__ count,
+__global__ void __launch_bounds__(256) k_commit(LocDev m, HashDev h, int display, const int4 *__restrict__ org, const int *__restrict__ count,
                                                 int *cnt, long long *stats_out)
 {
     gie_pdl_sync();
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
-        const int ti = __ldcg(&list[b]);
-        const int blk = __ldcg(&h.btab[ti]);
+        const int4 o = __ldcg(&org[b]);
+        const int blk = o.w;
         for (int v = threadIdx.x; v < 512; v += blockDim.x) {
             int3 c;
-            if (!block_voxel_local(m, h, ti, v, c)) continue;
+            if (!block_voxel_local(m, o, v, c)) continue;
             const int id = gie_lidx(m, c);
             const int8_t type = m.glb_type[id];
             if (type == GIE_VOX_UNKNOWN) continue;
@@ -920,6 +929,7 @@ int gie_wave_prepare(gie_hashmap *hm)
     GIE_CUDA_CHECK(cudaMalloc(&hm->decA_flags, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->snap_id, cap * 4));
     GIE_CUDA_CHECK(cudaMalloc(&hm->blk_list, hm->tab_entries * sizeof(int)));
+    GIE_CUDA_CHECK(cudaMalloc(&hm->blk_org, hm->tab_entries * sizeof(int4)));
     if (getenv("GIE_WAVE_TRACE")) {
         GIE_CUDA_CHECK(cudaMalloc(&hm->wave_trace, (size_t)TRACE_LEVELS * 10 * 8));
         GIE_CUDA_CHECK(cudaMemset(hm->wave_trace, 0, (size_t)TRACE_LEVELS * 10 * 8));
@@ -933,7 +943,7 @@ int gie_wave_list_blocks(gie_hashmap *hm)
     gie_locmap *lm = hm->lm;
     const int entries = (int)hm->tab_entries;
     GIE_CUDA_CHECK(cudaMemsetAsync(hm->blk_count, 0, sizeof(int), lm->stream));
-    gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, hm->blk_list, hm->blk_count);
+    gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, hm->blk_list, hm->blk_org, hm->blk_count);
     lm->launches++;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
@@ -950,9 +960,9 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
         StageTimer t(lm, GIE_ST_MARK_FRONTIER);
         GIE_CUDA_CHECK(cudaMemsetAsync(hm->barrier, 0, (hm->barrier_words + 64 + 32) * sizeof(unsigned int), lm->stream));   // + counters + blk_count
         const int entries = (int)hm->tab_entries;
-        gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, m, hm->d, entries, hm->blk_list, hm->blk_count);
-        gie_launch(k_mark_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, hm->blk_list, hm->blk_count);
-        gie_launch(k_frontiers, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, w, map_ct, hm->blk_list, hm->blk_count);
+        gie_launch(k_list_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, m, hm->d, entries, hm->blk_list, hm->blk_org, hm->blk_count);
+        gie_launch(k_mark_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, hm->blk_org, hm->blk_count);
+        gie_launch(k_frontiers, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, w, map_ct, hm->blk_org, hm->blk_count);
     }
     {
         StageTimer t(lm, GIE_ST_WAVES);
@@ -980,7 +990,7 @@ int gie_launch_merge(gie_hashmap *hm, int map_ct, int display)
     }
     {
         StageTimer t(lm, GIE_ST_COMMIT);
-        gie_launch(k_commit, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, display, hm->blk_list, hm->blk_count, hm->counters, hm->stats_host);
+        gie_launch(k_commit, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, m, hm->d, display, hm->blk_org, hm->blk_count, hm->counters, hm->stats_host);
     }
     lm->launches += 5;
     GIE_CUDA_CHECK(cudaGetLastError());
