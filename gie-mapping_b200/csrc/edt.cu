@@ -55,48 +55,10 @@ __global__ void __launch_bounds__(128) k_edt_ybits(LocDev m, unsigned long long 
     for (int v = 0; v < VEC; v++) out[v] = w[v];
 }
 
-// y pass, step 1, sparse form.  Every OCCUPIED voxel lies inside a block the OGM merge of this frame listed (hashmap.cu), and
-// the bit words that are set were set from the blocks the merge before listed: instead of reading the whole glb_type array
-// (1 B/voxel: 134 MB at 512^3, 1 GB at 1024^3) the previous list's words are cleared and this list's voxels are read.
-// Thread = one (z, x) column of a block (8 voxels along y, which may straddle two 32-row words).
-__global__ void __launch_bounds__(256) k_edt_ybits_clear(LocDev m, unsigned long long *__restrict__ ytab, int WY, int3 pvt, int3 tab_org, int3 tab_dim,
-                                                         const int *__restrict__ list, const int *__restrict__ count)
-{
-    gie_pdl_sync();
-    const int n = __ldcg(count);
-    const int sub = threadIdx.x >> 6, col = threadIdx.x & 63;     // 4 blocks per CTA pass
-    for (int b = blockIdx.x * 4 + sub; b < n; b += gridDim.x * 4) {
-        const int ti = __ldcg(&list[b]);
-        const int3 k = make_int3(ti % tab_dim.x, (ti / tab_dim.x) % tab_dim.y, ti / (tab_dim.x * tab_dim.y)) + tab_org;
-        const int x = k.x * 8 + (col & 7) - pvt.x, z = k.z * 8 + (col >> 3) - pvt.z, y0 = k.y * 8 - pvt.y;
-        if (x < 0 || x >= m.X || z < 0 || z >= m.Z || y0 + 7 < 0 || y0 >= m.Y) continue;
-        const int w0 = max(y0, 0) >> 5, w1 = min(y0 + 7, m.Y - 1) >> 5;
-        for (int wy = w0; wy <= w1; wy++) reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + wy) * m.X + x)[0] = 0;
-    }
-}
-__global__ void __launch_bounds__(256) k_edt_ybits_blocks(LocDev m, unsigned long long *__restrict__ ytab, int WY, int3 tab_org, int3 tab_dim,
-                                                          const int32_t *__restrict__ btab, const int *__restrict__ list, const int *__restrict__ count)
-{
-    gie_pdl_sync();
-    const int n = __ldcg(count);
-    const int sub = threadIdx.x >> 6, col = threadIdx.x & 63;
-    for (int b = blockIdx.x * 4 + sub; b < n; b += gridDim.x * 4) {
-        const int ti = __ldcg(&list[b]);
-        if (__ldcg(&btab[ti]) < 0) continue;                      // listed (touched) but never allocated: all UNKNOWN
-        const int3 k = make_int3(ti % tab_dim.x, (ti / tab_dim.x) % tab_dim.y, ti / (tab_dim.x * tab_dim.y)) + tab_org;
-        const int x = k.x * 8 + (col & 7) - m.pvt.x, z = k.z * 8 + (col >> 3) - m.pvt.z, y0 = k.y * 8 - m.pvt.y;
-        if (x < 0 || x >= m.X || z < 0 || z >= m.Z) continue;
-        uint32_t bits[2] = { 0, 0 };
-        const int w0 = max(y0, 0) >> 5;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int y = y0 + r;
-            if (y >= 0 && y < m.Y && m.glb_type[((size_t)z * m.Y + y) * m.X + x] == GIE_VOX_OCCUPIED) bits[(y >> 5) - w0] |= 1u << (y & 31);
-        }
-        if (bits[0]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0) * m.X + x), bits[0]);
-        if (bits[1]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0 + 1) * m.X + x), bits[1]);
-    }
-}
+// y pass, step 1, per frame: nothing in this file.  Every OCCUPIED voxel of the volume passes through the OGM merge of the
+// frame (hashmap.cu), which holds each visited block's types in shared memory: k_merge_ogm sets the bits of the block's columns
+// and k_clear_prev_blocks clears those of the previous merge's blocks (134 MB of glb_type at 512^3, 1 GB at 1024^3, are not read
+// back).  k_edt_ybits above remains for volumes whose glb_type was written from outside and for the first frame's state.
 
 // y pass, step 2: per column (z, x) link every word to the nearest set bit below / above it, and compact the columns of the
 // slice that hold an obstacle.  One CTA per slice, one thread per column; touches only ytab (0.25 B/voxel).
@@ -674,25 +636,13 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
     }
 }
 
-// y-pass bits: from the block lists of the OGM merges when they describe this frame (see k_edt_ybits_blocks), else from the whole array
+// y-pass bits: kept in step by the OGM merge (hashmap.cu) when the merge was the last to write glb_type, else from the whole array
 int launch_ybits(gie_locmap *lm, int WY)
 {
     const LocDev &m = lm->d;
     gie_hashmap *hm = lm->hm;
-    if (hm && hm->merge_serial > 0 && hm->blists[hm->bl_cur].valid && !lm->glb_type_foreign && !lm->slab_only && !getenv("GIE_YBITS_DENSE")) {
-        const gie_hashmap::BlockList &cur = hm->blists[hm->bl_cur], &prev = hm->blists[hm->bl_cur ^ 1];
-        const size_t words = (size_t)m.Z * WY * m.X;
-        if (lm->ytab_serial == hm->merge_serial - 1 && prev.valid)
-            gie_launch(k_edt_ybits_clear, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
-        else if (lm->ytab_serial != hm->merge_serial)
-            GIE_CUDA_CHECK(cudaMemsetAsync(lm->ytab, 0, words * 8, lm->stream));
-        else   // a second batch EDT on the same merge: clear what this merge's own list set
-            gie_launch(k_edt_ybits_clear, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, cur.pvt, cur.tab_org, hm->d.tab_dim, cur.list, cur.count);
-        gie_launch(k_edt_ybits_blocks, dim3(lm->num_sms * 4), dim3(256), 0, lm->stream, m, lm->ytab, WY, cur.tab_org, hm->d.tab_dim, hm->d.btab, cur.list, cur.count);
-        lm->ytab_serial = hm->merge_serial;
-        lm->launches++;
-        return GIE_OK;
-    }
+    // in step with the last OGM merge (hashmap.cu: cleared with the previous merge's blocks, set by k_merge_ogm): nothing to do
+    if (hm && hm->merge_serial > 0 && lm->ytab_serial == hm->merge_serial && !lm->glb_type_foreign && !lm->slab_only) return GIE_OK;
     lm->ytab_serial = -1;
     if (m.X % 4 == 0) gie_launch(k_edt_ybits<4>, dim3((m.X / 4 + 127) / 128, WY, m.Z), dim3(128), 0, lm->stream, m, lm->ytab, WY);
     else gie_launch(k_edt_ybits<1>, dim3((m.X + 127) / 128, WY, m.Z), dim3(128), 0, lm->stream, m, lm->ytab, WY);

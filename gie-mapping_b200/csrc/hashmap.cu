@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, 
 // the positions they had under the previous pivot — so those are cleared instead of the whole volume (134 MB per frame at
 // 512^3, 1 GB at 1024^3, against a few MB here).  One CTA pass per listed block, 2 voxels per thread.
 __global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_pvt, int3 tab_org, int3 tab_dim, const int *__restrict__ list,
-                                                           const int *__restrict__ count)
+                                                           const int *__restrict__ count, unsigned long long *__restrict__ ytab, int WY)
 {
     gie_pdl_sync();
     const int n = __ldcg(count);
@@ -132,18 +132,25 @@ __global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_p
             const int v = threadIdx.x + 256 * u;
             const int3 c = make_int3(k.x * 8 + (v & 7), k.y * 8 + ((v >> 3) & 7), k.z * 8 + (v >> 6)) - prev_pvt;
             if (gie_inside_loc(m, c)) m.glb_type[gie_lidx(m, c)] = GIE_VOX_UNKNOWN;
+            // the batch EDT's y-pass bits (edt.cu) of this block's columns go with it: k_merge_ogm sets this frame's
+            if (ytab && (v & 0x38) == 0 && c.x >= 0 && c.x < m.X && c.z >= 0 && c.z < m.Z && c.y + 7 >= 0 && c.y < m.Y) {
+                const int w0 = max(c.y, 0) >> 5, w1 = min(c.y + 7, m.Y - 1) >> 5;
+                for (int wy = w0; wy <= w1; wy++) reinterpret_cast<uint32_t *>(ytab + ((size_t)c.z * WY + wy) * m.X + c.x)[0] = 0;
+            }
         }
     }
 }
 
 template <bool PNTCLD>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
-                                                   const int *__restrict__ list, const int *__restrict__ count)
+                                                   const int *__restrict__ list, const int *__restrict__ count,
+                                                   unsigned long long *__restrict__ ytab, int WY)
 {
     gie_pdl_sync();
     using barrier_t = cuda::barrier<cuda::thread_scope_block>;
     __shared__ int s_blk;
     __shared__ alignas(16) int8_t s_type[512];
+    __shared__ int8_t s_new[512];   // the block's types after the merge (voxels inside the volume), for the y-pass bits
     __shared__ alignas(16) uint8_t s_occ[512];
 #pragma nv_diag_suppress static_var_with_dynamic_init
     __shared__ barrier_t bar;
@@ -224,6 +231,28 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
                 if (stream && type != old_type) h.dirty[blk] = 1;
             }
             m.glb_type[id[u]] = type;
+            s_new[v] = type;
+        }
+        // The batch EDT starts from OCCUPIED bits packed along y (ytab, edt.cu).  Every OCCUPIED voxel of the volume passes
+        // through here, so the bits are set here, from the types the CTA holds anyway, instead of by a kernel that reads
+        // glb_type back: thread = one (z, x) column of the block, 8 voxels along y, which may straddle two 32-row words.
+        if (ytab) {
+            __syncthreads();
+            if (threadIdx.x < 64) {
+                const int col = threadIdx.x;
+                const int x = k.x * 8 + (col & 7) - m.pvt.x, z = k.z * 8 + (col >> 3) - m.pvt.z, y0 = k.y * 8 - m.pvt.y;
+                if (x >= 0 && x < m.X && z >= 0 && z < m.Z) {
+                    uint32_t bits[2] = { 0, 0 };
+                    const int w0 = max(y0, 0) >> 5;
+#pragma unroll
+                    for (int r = 0; r < 8; r++) {
+                        const int y = y0 + r;
+                        if (y >= 0 && y < m.Y && s_new[(col >> 3) * 64 + r * 8 + (col & 7)] == GIE_VOX_OCCUPIED) bits[(y >> 5) - w0] |= 1u << (y & 31);
+                    }
+                    if (bits[0]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0) * m.X + x), bits[0]);
+                    if (bits[1]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0 + 1) * m.X + x), bits[1]);
+                }
+            }
         }
         __syncthreads();   // the staging buffers are free for the next block
     }
@@ -312,9 +341,16 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     const int entries = (int)hm->tab_entries;
     // UNKNOWN wherever no block exists: clear what the previous merge may have written (the whole array only the first time
     // and after a test upload), then list the blocks of this merge into the other buffer
+    // The y-pass bits of the batch EDT (lm->ytab, low word of every entry) are kept in step with glb_type: cleared with the
+    // previous merge's blocks, set by k_merge_ogm.  They are in step when the last thing that wrote them was the previous merge.
     gie_hashmap::BlockList &prev = hm->blists[hm->bl_cur];
+    const int WY = (lm->d.Y + 31) / 32;
+    unsigned long long *ytab = (lm->ytab && !getenv("GIE_YBITS_DENSE")) ? lm->ytab : nullptr;
+    const bool ytab_in_step = ytab && prev.valid && !lm->glb_type_foreign && lm->ytab_serial == hm->merge_serial;
+    if (ytab && !ytab_in_step) GIE_CUDA_CHECK(cudaMemsetAsync(ytab, 0, (size_t)lm->d.Z * WY * lm->d.X * 8, lm->stream));
     if (prev.valid && !lm->glb_type_foreign) {
-        gie_launch(k_clear_prev_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count);
+        gie_launch(k_clear_prev_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count,
+                   ytab_in_step ? ytab : (unsigned long long *)nullptr, WY);
         lm->launches++;
     } else GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));
     lm->glb_type_foreign = false;
@@ -325,8 +361,9 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     GIE_CUDA_CHECK(cudaMemsetAsync(cur.count, 0, sizeof(int), lm->stream));
     gie_launch(k_list_merge_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, cur.list, cur.count);
     const int grid = lm->num_sms * 16;
-    if (input_pntcld) gie_launch(k_merge_ogm<true>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
-    else gie_launch(k_merge_ogm<false>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count);
+    if (input_pntcld) gie_launch(k_merge_ogm<true>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY);
+    else gie_launch(k_merge_ogm<false>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY);
+    lm->ytab_serial = ytab ? hm->merge_serial : -1;
     lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
     return GIE_OK;
