@@ -547,7 +547,7 @@ def main():
             d["dram_gbs"] = traffic[k] / (prof[k] * 1e-3) / 1e9      # measured bytes of one ncu capture / live event time
         return d
 
-    roofline = {"bound": "hbm", "kernel": "batch_dt = k_edt_ybits + k_edt_ycols + k_edt_slices + k_edt_xsweep + k_edt_zsweep (EDT_OCC::batchEDTUpdate)",
+    roofline = {"bound": "hbm", "kernel": "batch_dt = k_edt_ycols + k_edt_slices + k_edt_xsweep + k_edt_zsweep (EDT_OCC::batchEDTUpdate; the y-pass bits are set by the OGM merge)",
                 "achieved": achieved, "peak": peak, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs, burst copy)", "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic.get("batch_dt"), "traffic_source": traffic.get("_file"),
                 "algorithmic_bytes_per_voxel": bpv, "algorithmic_bytes_per_launch": bpv * nvox,

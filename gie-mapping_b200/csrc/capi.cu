@@ -152,7 +152,7 @@ int gie_locmap_destroy(gie_locmap *lm)
     cudaFree(m.ray_count); cudaFree(m.inst_type); cudaFree(m.glb_type); cudaFree(m.edt); cudaFree(m.aux);
     cudaFree(m.coc_aux); cudaFree(m.wave_layer); cudaFree(m.pair); cudaFree(m.nbr_flag);
     if (!lm->edt_inputs_aliased) { cudaFree(lm->ytab); cudaFree(lm->col_list); cudaFree(lm->edt_meta); }
-    cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
+    cudaFree(lm->slice_has); cudaFree(lm->g2); cudaFree(lm->cxy); cudaFree(lm->stack_scratch); cudaFree(lm->work_counters);
     for (int i = 0; i < lm->n_ipc_opened; i++) cudaIpcCloseMemHandle(lm->ipc_opened[i]);
     cudaFree(lm->stage_dev); cudaFree(lm->ray_scratch);
     for (int i = 0; i < GIE_ST_COUNT; i++) for (int j = 0; j < 2; j++) if (lm->ev[i][j]) cudaEventDestroy(lm->ev[i][j]);

@@ -63,11 +63,16 @@ __global__ void __launch_bounds__(128) k_edt_ybits(LocDev m, unsigned long long 
 // y pass, step 2: per column (z, x) link every word to the nearest set bit below / above it, and compact the columns of the
 // slice that hold an obstacle.  One CTA per slice, one thread per column; touches only ytab (0.25 B/voxel).
 __global__ void __launch_bounds__(1024) k_edt_ycols(LocDev m, unsigned long long *__restrict__ ytab, int WY,
-                                                    int *__restrict__ col_list, int *__restrict__ n_cols)
+                                                    int *__restrict__ col_list, int *__restrict__ n_cols, const int *__restrict__ slice_has)
 {
     gie_pdl_sync();
     __shared__ int warp_cnt[32];
     const int x = threadIdx.x, z = blockIdx.x;
+    // the OGM merge flags the slices it set a bit in: nine slices in ten hold none and their 16 x X words need not be read
+    if (slice_has && __ldcg(&slice_has[z]) == 0) {
+        if (x == 0) n_cols[z] = 0;
+        return;
+    }
     const int lane = x & 31, wid = x >> 5;
     bool any = false;
     if (x < m.X) {
@@ -637,6 +642,11 @@ k_edt_zsweep(LocDev m, const int32_t *__restrict__ g2, const int32_t *__restrict
 }
 
 // y-pass bits: kept in step by the OGM merge (hashmap.cu) when the merge was the last to write glb_type, else from the whole array
+// slice flags are valid when the merge was the last to write the bits (launch_ybits found them in step)
+const int *ybits_slice_flags(gie_locmap *lm)
+{
+    return lm->hm && lm->ytab_serial >= 0 && lm->ytab_serial == lm->hm->merge_serial ? lm->slice_has : nullptr;
+}
 int launch_ybits(gie_locmap *lm, int WY)
 {
     const LocDev &m = lm->d;
@@ -661,6 +671,8 @@ int gie_edt_prepare(gie_locmap *lm)
     GIE_CUDA_CHECK(cudaMalloc(&lm->cxy, slab_voxels * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->col_list, (size_t)m.Z * m.X * 4));
     GIE_CUDA_CHECK(cudaMalloc(&lm->edt_meta, (size_t)(2 * m.Z + 8) * 4));   // n_cols[Z], slice_list[Z], n_slices
+    GIE_CUDA_CHECK(cudaMalloc(&lm->slice_has, (size_t)m.Z * 4));
+    GIE_CUDA_CHECK(cudaMemset(lm->slice_has, 0, (size_t)m.Z * 4));
     int L = m.X > m.Z ? m.X : m.Z;
     // serial z sweep: persistent CTAs of ZS_WARPS warps, 32 warps per SM; every warp pulls (row, 32 x) items
     int n_items = m.ysn * ((m.X + 31) / 32);
@@ -742,7 +754,7 @@ int gie_launch_edt_xy(gie_locmap *lm)
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     GIE_CUDA_CHECK(cudaMemsetAsync(lm->work_counters, 0, 4 * sizeof(int), lm->stream));
     launch_ybits(lm, WY);
-    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols, ybits_slice_flags(lm));
     gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, (int *)nullptr);
     launch_xsweep(lm, WY, n_cols, slice_list, n_slices);
     lm->launches += 4;
@@ -789,7 +801,7 @@ int gie_launch_edt_pack(gie_locmap *lm, unsigned long long *ytab_compact, int *c
     int *n_cols = lm->edt_meta, *slice_list = lm->edt_meta + m.Z, *n_slices = lm->edt_meta + 2 * m.Z;
     StageTimer t(lm, GIE_ST_EDT_PACK);
     launch_ybits(lm, WY);
-    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+    gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols, ybits_slice_flags(lm));
     gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, (int *)nullptr);
     lm->launches += 3;
     if (ytab_compact && col_compact) {
@@ -828,7 +840,7 @@ int gie_launch_batch_edt(gie_locmap *lm)
     {
         StageTimer t(lm, GIE_ST_EDT_PACK);
         launch_ybits(lm, WY);
-        gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols);
+        gie_launch(k_edt_ycols, dim3(m.Z), dim3(((m.X + 31) / 32) * 32), 0, lm->stream, m, lm->ytab, WY, lm->col_list, n_cols, ybits_slice_flags(lm));
         gie_launch(k_edt_slices, dim3(1), dim3(((m.Z + 31) / 32) * 32), 0, lm->stream, m.Z, n_cols, slice_list, n_slices, lm->work_counters);
     }
     {

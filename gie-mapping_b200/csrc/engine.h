@@ -19,6 +19,7 @@ struct gie_locmap {
     int32_t *cxy = nullptr;               // [Z][Y][X] cocx | cocy << 16
     int *col_list = nullptr;              // [Z][X] columns of each slice that hold an obstacle (ascending)
     int *edt_meta = nullptr;              // n_cols[Z], slice_list[Z], n_slices
+    int *slice_has = nullptr;             // [Z] 1 = the OGM merge set a y-pass bit in this slice (valid while ytab is in step with the merge)
     unsigned long long *stack_scratch = nullptr;
     size_t stack_scratch_entries = 0;
     int edt_ctas = 0;                     // persistent grid of the z sweep

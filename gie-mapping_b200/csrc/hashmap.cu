@@ -120,9 +120,12 @@ __global__ void __launch_bounds__(256) k_list_merge_blocks(LocDev m, HashDev h, 
 // the positions they had under the previous pivot — so those are cleared instead of the whole volume (134 MB per frame at
 // 512^3, 1 GB at 1024^3, against a few MB here).  One CTA pass per listed block, 2 voxels per thread.
 __global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_pvt, int3 tab_org, int3 tab_dim, const int *__restrict__ list,
-                                                           const int *__restrict__ count, unsigned long long *__restrict__ ytab, int WY)
+                                                           const int *__restrict__ count, unsigned long long *__restrict__ ytab, int WY,
+                                                           int *__restrict__ slice_has)
 {
     gie_pdl_sync();
+    if (ytab && blockIdx.x == 0)
+        for (int z = threadIdx.x; z < m.Z; z += blockDim.x) slice_has[z] = 0;   // k_merge_ogm flags the slices it sets a bit in
     const int n = __ldcg(count);
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const int ti = __ldcg(&list[b]);
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(256) k_clear_prev_blocks(LocDev m, int3 prev_p
 template <bool PNTCLD>
 __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_ct, int stream, int n_obs, const float *__restrict__ obs,
                                                    const int *__restrict__ list, const int *__restrict__ count,
-                                                   unsigned long long *__restrict__ ytab, int WY)
+                                                   unsigned long long *__restrict__ ytab, int WY, int *__restrict__ slice_has)
 {
     gie_pdl_sync();
     using barrier_t = cuda::barrier<cuda::thread_scope_block>;
@@ -251,6 +254,7 @@ __global__ void __launch_bounds__(256) k_merge_ogm(LocDev m, HashDev h, int map_
                     }
                     if (bits[0]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0) * m.X + x), bits[0]);
                     if (bits[1]) atomicOr(reinterpret_cast<uint32_t *>(ytab + ((size_t)z * WY + w0 + 1) * m.X + x), bits[1]);
+                    if (bits[0] | bits[1]) slice_has[z] = 1;
                 }
             }
         }
@@ -347,10 +351,13 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     const int WY = (lm->d.Y + 31) / 32;
     unsigned long long *ytab = (lm->ytab && !getenv("GIE_YBITS_DENSE")) ? lm->ytab : nullptr;
     const bool ytab_in_step = ytab && prev.valid && !lm->glb_type_foreign && lm->ytab_serial == hm->merge_serial;
-    if (ytab && !ytab_in_step) GIE_CUDA_CHECK(cudaMemsetAsync(ytab, 0, (size_t)lm->d.Z * WY * lm->d.X * 8, lm->stream));
+    if (ytab && !ytab_in_step) {
+        GIE_CUDA_CHECK(cudaMemsetAsync(ytab, 0, (size_t)lm->d.Z * WY * lm->d.X * 8, lm->stream));
+        GIE_CUDA_CHECK(cudaMemsetAsync(lm->slice_has, 0, (size_t)lm->d.Z * 4, lm->stream));
+    }
     if (prev.valid && !lm->glb_type_foreign) {
         gie_launch(k_clear_prev_blocks, dim3(lm->num_sms * 8), dim3(256), 0, lm->stream, lm->d, prev.pvt, prev.tab_org, hm->d.tab_dim, prev.list, prev.count,
-                   ytab_in_step ? ytab : (unsigned long long *)nullptr, WY);
+                   ytab_in_step ? ytab : (unsigned long long *)nullptr, WY, lm->slice_has);
         lm->launches++;
     } else GIE_CUDA_CHECK(cudaMemsetAsync(lm->d.glb_type, 0, (size_t)lm->d.N, lm->stream));
     lm->glb_type_foreign = false;
@@ -361,8 +368,8 @@ int gie_launch_update_ogm(gie_hashmap *hm, int input_pntcld, int map_ct, int str
     GIE_CUDA_CHECK(cudaMemsetAsync(cur.count, 0, sizeof(int), lm->stream));
     gie_launch(k_list_merge_blocks, dim3(std::min((entries + 255) / 256, lm->num_sms * 8)), dim3(256), 0, lm->stream, lm->d, hm->d, entries, cur.list, cur.count);
     const int grid = lm->num_sms * 16;
-    if (input_pntcld) gie_launch(k_merge_ogm<true>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY);
-    else gie_launch(k_merge_ogm<false>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY);
+    if (input_pntcld) gie_launch(k_merge_ogm<true>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY, lm->slice_has);
+    else gie_launch(k_merge_ogm<false>, dim3(grid), dim3(256), 0, lm->stream, lm->d, hm->d, map_ct, stream, n_obs, obs, cur.list, cur.count, ytab, WY, lm->slice_has);
     lm->ytab_serial = ytab ? hm->merge_serial : -1;
     lm->launches += 2;
     GIE_CUDA_CHECK(cudaGetLastError());
