@@ -1,6 +1,6 @@
 # per-kernel durations of one frame (frame 20 of cfg4), about 1 GPU-minute
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 379 -c 22 --csv --log-file gpurun_out/launch_list_cur.csv python scratch/prof_run.py cfg4 21 > gpurun_out/launch_list_cur.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:^k_ -s 339 -c 20 --csv --log-file gpurun_out/launch_list_cur.csv python scratch/prof_run.py cfg4 21 > gpurun_out/launch_list_cur.log 2>&1
 python - <<'PY'
 import csv
 rows=list(csv.reader(open('gpurun_out/launch_list_cur.csv')))

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 ( time timeout 1700 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_final.log 2>&1
 tail -4 gpurun_out/pytest_gpu_final.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; tail -1 gpurun_out/smoke_final.log
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_ -s 379 -c 22 -o gpurun_out/prof_full_final -f python scratch/prof_run.py cfg4 21 > gpurun_out/ncu_full_final.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:^k_ -s 339 -c 20 -o gpurun_out/prof_full_final -f python scratch/prof_run.py cfg4 21 > gpurun_out/ncu_full_final.log 2>&1
 tail -1 gpurun_out/ncu_full_final.log
 ncu -i gpurun_out/prof_full_final.ncu-rep --page raw --csv > gpurun_out/ncu_full_final_raw.csv 2>/dev/null
 for k in k_edt_xsweep k_edt_zsweep k_pc_apply k_pc_walk k_frontiers k_waves; do ncu -i gpurun_out/prof_full_final.ncu-rep --page details --kernel-name regex:$k 2>/dev/null | grep -E "Duration|Throughput|Issue|Eligible|Occupancy|Active Warps|Registers|Shared Memory|Hit Rate|Cycles Per|Section" | head -60 > gpurun_out/ncu_details_final_$k.txt; done
