@@ -44,6 +44,44 @@ def test_product_never_imports_oracle():
                 assert not banned.search(src), f"{f} references the oracle"
 
 
+def test_dependent_launch_chain_is_transitive():
+    """Every kernel launched through gie_launch (programmatic dependent launch) must execute
+    griddepcontrol.wait before anything else — in particular before any early return: a CTA that leaves without waiting lets
+    the NEXT kernel of the stream start while the PREVIOUS one is still running.  Checked on the sources (the call is the
+    first statement of the kernel body) and on the built library (PREEXIT / ACQBULK in the SASS of each such kernel)."""
+    csrc = os.path.join(ROOT, "gie-mapping_b200", "csrc")
+    launched, bodies = set(), {}
+    for f in os.listdir(csrc):
+        if not f.endswith(".cu"):
+            continue
+        src = open(os.path.join(csrc, f)).read()
+        launched |= set(re.findall(r"gie_launch\(\s*(k_[a-z0-9_]+)", src))
+        for m in re.finditer(r"__global__[^;{]*?\b(k_[a-z0-9_]+)\s*\(", src):
+            i, depth = m.end(), 1
+            while depth:
+                depth += {"(": 1, ")": -1}.get(src[i], 0)
+                i += 1
+            j = src.index("{", i)
+            bodies[m.group(1)] = src[j + 1:j + 200].lstrip()
+    assert len(launched) >= 15
+    for k in sorted(launched):
+        assert bodies[k].startswith("gie_pdl_sync();"), f"{k}: gie_pdl_sync() must be the first statement"
+    lib = os.path.join(ROOT, "gie-mapping_b200", "libgie_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    cur, seen = None, {}
+    for line in sass.splitlines():
+        m = re.search(r"Function : \S*?(k_[a-z0-9_]+)", line)
+        if m:
+            cur = m.group(1) if m.group(1) in launched else None   # the mangled name continues in upper case
+            continue
+        if cur and ("ACQBULK" in line or "PREEXIT" in line):
+            seen.setdefault(cur, set()).add("ACQBULK" if "ACQBULK" in line else "PREEXIT")
+    for k in sorted(launched):
+        assert seen.get(k) == {"ACQBULK", "PREEXIT"}, f"{k}: griddepcontrol instructions missing from the SASS ({seen.get(k)})"
+
+
 def test_scenes_are_deterministic(gie):
     cfg = gie.scenes.small_config("cfg4", (48, 48, 24))
     a = gie.scenes.make_frames(cfg, 3, dynamic=True)
