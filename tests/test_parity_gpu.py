@@ -786,3 +786,31 @@ def test_reference_node_starts(gie, tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path), timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "Local Map initialized" in res.stdout or "data_case" in res.stdout
+
+
+@pytest.mark.parametrize("switch", ["GIE_NO_PDL", "GIE_YBITS_DENSE", "GIE_WAVE_NO_LOCAL"])
+def test_diagnostic_switches_keep_parity(switch):
+    """The environment switches of INTEGRATION.md section 7 turn a mechanism off (programmatic dependent launch, y-pass bits kept
+    in step by the OGM merge, cluster-local wave C); results must not change.  They are read once per process, hence a
+    subprocess: the full pipeline on a ragged dynamic scene against the oracle, every array of every frame."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import load_pkg\n"
+        "import test_parity_gpu as T\n"
+        "gie = load_pkg()\n"
+        "from oracle import oracle_py as oracle\n"
+        "oracle.build()\n"
+        "cfg = gie.scenes.small_config('cfg4', (64, 40, 33), cutoff_grids_sq=100)\n"
+        "frames = gie.scenes.make_frames(cfg, 5, dynamic=True)\n"
+        "mp, om = gie.Mapper(cfg), oracle.OracleMapper(cfg)\n"
+        "for k, f in enumerate(frames):\n"
+        "    mp.publishMap(f); om.publishMap(f)\n"
+        "    T._cmp_frame(gie, mp, om, 'frame %%d' %% k)\n"
+        "mp.close(); om.close(); print('switch parity OK')\n" % (os.path.join(root, "tests"), root))
+    env = dict(os.environ, **{switch: "1"})
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=root)
+    assert res.returncode == 0 and "switch parity OK" in res.stdout, res.stdout[-1500:] + res.stderr[-1500:]
