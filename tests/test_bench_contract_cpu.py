@@ -15,8 +15,10 @@ def _line(name):
     return json.loads(open(path).read().strip().splitlines()[-1])
 
 
-def test_ours_line_has_the_contract_keys():
-    d = _line("r01_bench_ours_final.json")
+@pytest.mark.parametrize("name", ["r01_bench_ours_final.json", "r02_bench_ours_final.json", "r02_bench_ours_cfg1.json",
+                                  "r02_bench_ours_cfg2.json", "r02_bench_ours_cfg3.json"])
+def test_ours_line_has_the_contract_keys(name):
+    d = _line(name)
     for k in ["metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
               "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"]:
         assert k in d, k
@@ -38,9 +40,38 @@ def test_ours_line_has_the_contract_keys():
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
 
 
-def test_reference_line_has_the_contract_keys():
-    d = _line("r01_bench_reference_final.json")
+@pytest.mark.parametrize("name", ["r01_bench_reference_final.json", "r02_bench_reference_final.json", "r02_bench_reference_cfg1.json",
+                                  "r02_bench_reference_cfg2.json", "r02_bench_reference_cfg3.json", "r02_bench_reference_cfg5.json"])
+def test_reference_line_has_the_contract_keys(name):
+    d = _line(name)
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["unit"] == "frames/s"
     assert "workload" in d["config"]
+
+
+@pytest.mark.parametrize("tag", ["final", "cfg1", "cfg2", "cfg3"])
+def test_both_arms_time_the_same_workload(tag):
+    """The two arms of a configuration are compared by the driver: they must describe the same workload, up to the number of
+    points per frame (a mean over the frames each arm timed: 50 after 10 warm-up frames against 50 after 5)."""
+    import re
+    ours, ref = _line(f"r02_bench_ours_{tag}.json"), _line(f"r02_bench_reference_{tag}.json")
+    strip = lambda w: re.sub(r"\d+ points/frame", "N points/frame", w)
+    assert strip(ours["config"]["workload"]) == strip(ref["config"]["workload"])
+    assert ours["metric"] == ref["metric"] and ours["unit"] == ref["unit"] and ours["higher_is_better"] == ref["higher_is_better"]
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_sharded_lines(n):
+    """bench.py --gpus N times ONE volume sharded over N GPUs (strong scaling) and carries rank 0's single-GPU time for the same
+    frames; the reference arm of the same launch runs the same cfg5 volume."""
+    d = _line(f"r02_bench_sharded_n{n}.json")
+    assert d["n_gpus"] == n and d["scaling"] == "strong" and d["unit"] == "frames/s" and d["gpu_launches"] > 0
+    assert abs(d["value"] - 1000.0 / d["ms_per_step"]) / d["value"] < 1e-6
+    single = d["single_gpu_same_workload"]
+    assert abs(d["strong_scaling"]["speedup"] - single["ms_per_step"] / d["ms_per_step"]) < 1e-6
+    assert abs(d["strong_scaling"]["efficiency"] - d["strong_scaling"]["speedup"] / n) < 1e-9
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and 0 < d["e2e"]["value"] <= d["value"] * 1.001
+    assert d["broadcast_bytes_per_frame"] > 0 and d["slab_sweeps_ms_max_over_ranks"] < d["ms_per_step"]
+    ref = _line("r02_bench_reference_cfg5.json")
+    assert ref["config"]["workload"].split(",")[0] == d["config"]["workload"].split(",")[0]      # "cfg5: 1024x1024x1016 @ 0.1 m"
