@@ -9,18 +9,18 @@
 // argmin_k (z-k)^2 + g2(k) ties -> smallest k.  Output _aux = dist_sq, _coc_idx_aux = x | y<<11 | z<<22 (local).
 //
 // Mechanism (no transposes, no global s/t/g arrays):
-//   k_edt_ycols : one CTA per slice z, one thread per column x.  Packs OCCUPIED bits along y into 32-bit words plus, per
-//                 word, the nearest set bit below / above it -> ytab[z][wy][x] (0.25 B/voxel); the y pass is never
-//                 materialised.  Also compacts the columns of the slice that hold an obstacle.  A column without one is
-//                 the reference's "_max_width" sentinel for EVERY row of the slice and can never win the x sweep while a
-//                 real column exists ((X+Y+Z)^2 exceeds any real candidate), so the x sweep only visits real columns, and
-//                 slices without any obstacle are skipped altogether (the z sweep never reads them).
-//   k_edt_xsweep: one warp = 32 consecutive rows y of one real slice.  Lane y derives g1(u,y) from the warp-uniform ytab
-//                 entry with two bit scans, runs the lower-envelope scan along x (stack top in registers, the next 16
-//                 entries per lane in a shared-memory ring, deeper entries in an L2-resident per-warp scratch), and emits
-//                 its outputs through a 32x16 shared-memory tile so that global stores are x-contiguous.
-//   k_edt_zsweep: one warp = 32 consecutive x of one row y; the same scan along z over the real slices only, naturally
-//                 coalesced; gathers (cocx,cocy) of the winning slice and writes the final packed result.
+//   y bits      : OCCUPIED bits packed along y (low word of ytab[z][y/32][x]) are kept in step by the OGM merge (hashmap.cu);
+//                 k_edt_ybits rebuilds them from glb_type only when the array was written from outside.
+//   k_edt_ycols : one CTA per slice z the merge flagged, one thread per column x.  Links every word to the nearest set bit
+//                 below / above it (0.25 B/voxel); the y pass is never materialised.  Also compacts the columns of the slice
+//                 that hold an obstacle.  A column without one is the reference's "_max_width" sentinel for EVERY row of
+//                 the slice and can never win the x sweep while a real column exists ((X+Y+Z)^2 exceeds any real candidate),
+//                 so the x sweep only visits real columns, and slices without any obstacle are skipped altogether.
+//   k_edt_xsweep: banded lower envelope.  Item = (real slice, 16 rows); thread = (band of real columns, row).  Forward per
+//                 band with the reference's sequential push, bands merged pairwise by searching the cut between two
+//                 envelopes, backward per x range through a 16 x 8 tile so that global stores are x-contiguous.
+//   k_edt_zsweep: one warp = 32 consecutive x of one row y; the sequential scan along z over the real slices only, naturally
+//                 coalesced; an entry carries the closest-obstacle word it will store; streaming stores of aux / coc_aux.
 // Persistent CTAs (a multiple of the SM count) pull work items from an atomic counter.
 #include "engine.h"
 #include <algorithm>
