@@ -12,8 +12,9 @@
 // Mechanism: ONE persistent cooperative kernel runs wave A, B and C back to back with a device-side grid barrier
 // between BFS levels and global ring queues; there is no host round trip inside a frame.  The relaxation is a 64-bit
 // atomicMin on (dist_sq << 32 | coc id), which also makes the result independent of thread scheduling — the reference
-// is schedule dependent here; the deterministic rules D1-D3, D5 are listed in DESIGN.md §3.2 and are restated
-// identically by the CPU oracle.
+// resolves equal-distance offers by arrival order (its distances are repeatable run to run all the same, measured on a B200);
+// the deterministic rules D1-D3, D5 and what they cost in agreement (54 of 1.5 M known voxel-frames of the pinned fixtures)
+// are in DESIGN.md §3.2 and are restated identically by the CPU oracle.
 #include "engine.h"
 #include <cooperative_groups.h>
 #include <algorithm>
